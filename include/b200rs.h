@@ -1,0 +1,144 @@
+/*
+ * b200rs.h -- C ABI of libb200rs.so: the B200 (sm_100a) implementation of OCLRadixSort's
+ * data-parallel hot path (LSD radix sort of u32 keys and u32/u32 pairs, exclusive u32 scan).
+ *
+ * The reference has no FFI layer; its boundary is the header-level C++ API
+ *     adl::DeviceUtils / adl::Device / adl::Buffer<T>      (Adl/Adl.h:71-222)
+ *     Tahoe::Pprims::radixSort / Pprims::scan               (Tahoe/ParallelPrimitives/Pprims.h:35-41)
+ * (paths relative to the reference tree).  The drop-in C++ headers under include/Adl and
+ * include/Tahoe keep those spellings and forward to the entry points declared here; each entry
+ * point cites the reference interface it stands in for.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - Every function returns int: 0 = B200RS_OK, > 0 = a cudaError_t value, < 0 = a B200RS_ERR_* code.
+ *     Nothing throws; nothing falls back to the CPU.
+ *   - A b200rs_device owns (or borrows) ONE CUDA stream; all work is enqueued on it in order and
+ *     is asynchronous with respect to the host unless the function name ends in _sync or _host
+ *     (reference contract: one in-order queue, visibility after DeviceUtils::waitForCompletion,
+ *     Adl/CL/AdlCL.inl:303,567-570).
+ *   - Not thread-safe per handle (neither is the reference: Pprims scratch, KernelManager map).
+ *   - Device pointers must be 4-byte (keys, scan) / 8-byte (pairs) aligned; 16-byte alignment
+ *     (any cudaMalloc pointer) enables the 128-bit paths.
+ */
+#ifndef B200RS_H
+#define B200RS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RS_VERSION 100 /* 0.1.0 */
+
+#define B200RS_OK 0
+#define B200RS_ERR_INVALID_ARGUMENT (-1) /* null handle/pointer, sort_bits outside [0,32], misaligned pointer */
+#define B200RS_ERR_TEMP_TOO_SMALL (-2)   /* *temp_bytes smaller than the size query returned */
+#define B200RS_ERR_NO_DEVICE (-3)        /* no CUDA device / device index out of range */
+#define B200RS_ERR_UNSUPPORTED_ARCH (-4) /* device is not compute capability 10.x (binary is sm_100a only) */
+#define B200RS_ERR_TOO_LARGE (-5)        /* n beyond what the entry point supports */
+#define B200RS_ERR_OUT_OF_MEMORY (-6)    /* internal scratch allocation failed */
+#define B200RS_ERR_CAPACITY (-7)         /* distributed sort: a rank's receive buffer is too small */
+
+typedef struct b200rs_device b200rs_device; /* opaque */
+
+/* 8-byte AoS pair, key first: Tahoe::SortData (Tahoe/Algorithm/Sort/RadixSort.h:10-21) and
+ * Tahoe::uint2 {x=key,y=value} (Tahoe/Math/Math.h:175-188; Pprims.h:37). */
+typedef struct b200rs_pair { uint32_t key; uint32_t value; } b200rs_pair;
+
+int b200rs_version(void);
+const char* b200rs_error_string(int code);
+
+/* ---- device: replaces adl::DeviceUtils / adl::DeviceCL -------------------------------------- */
+
+/* DeviceUtils::getNDevices(TYPE_CL), Adl/Adl.inl:8-23. */
+int b200rs_device_count(int* count);
+/* DeviceUtils::allocate(TYPE_CL, cfg) -> DeviceCL::initialize, Adl/Adl.inl:73-98, Adl/CL/AdlCL.inl:148-345.
+ * Creates one in-order non-blocking stream (the cl_command_queue of AdlCL.inl:303). */
+int b200rs_device_create(int device_idx, b200rs_device** dev);
+/* Same, but enqueue on a stream the caller owns (cudaStream_t; e.g. torch's current stream). */
+int b200rs_device_create_on_stream(int device_idx, void* cuda_stream, b200rs_device** dev);
+/* DeviceUtils::deallocate, Adl/Adl.inl:100-105 (the used-memory assert lives in the C++ header). */
+int b200rs_device_destroy(b200rs_device* dev);
+/* DeviceUtils::waitForCompletion(device) = clFinish, Adl/CL/AdlCL.inl:567-570. */
+int b200rs_device_sync(b200rs_device* dev);
+/* DeviceUtils::getNCUs, Adl/Adl.inl:45-71 / AdlCL.inl:704-709 (compute units -> SMs). */
+int b200rs_device_num_sms(const b200rs_device* dev, int* num_sms);
+/* Device::getDeviceName, Adl/Adl.h:135. */
+int b200rs_device_name(const b200rs_device* dev, char name_out[128]);
+int b200rs_device_index(const b200rs_device* dev, int* device_idx);
+int b200rs_device_mem_info(const b200rs_device* dev, size_t* free_bytes, size_t* total_bytes);
+/* The cudaStream_t work is enqueued on (for event timing by the caller). */
+void* b200rs_device_stream(const b200rs_device* dev);
+
+/* ---- memory: replaces DeviceCL::allocate/deallocate/copy, Adl/CL/AdlCL.inl:356-510 ------------ */
+
+int b200rs_malloc(b200rs_device* dev, size_t bytes, void** ptr);           /* clCreateBuffer, AdlCL.inl:356-410 */
+int b200rs_free(b200rs_device* dev, void* ptr);                            /* clReleaseMemObject, :412-439 */
+int b200rs_host_alloc(b200rs_device* dev, size_t bytes, void** host_ptr);  /* pinned staging for map/unmap, :544-565 */
+int b200rs_host_free(b200rs_device* dev, void* host_ptr);
+int b200rs_memcpy_h2d(b200rs_device* dev, void* dst, const void* host_src, size_t bytes); /* Buffer::write, :489-510 */
+int b200rs_memcpy_d2h(b200rs_device* dev, void* host_dst, const void* src, size_t bytes); /* Buffer::read,  :466-487 */
+int b200rs_memcpy_d2d(b200rs_device* dev, void* dst, const void* src, size_t bytes);      /* Buffer::write(Buffer&), :441-464 */
+int b200rs_memset(b200rs_device* dev, void* ptr, int byte_value, size_t bytes);           /* Buffer::clear, :512-542 */
+
+/* ---- the hot path: replaces Pprims::radixSort / Pprims::scan ---------------------------------- */
+
+/*
+ * Temp storage is CUB-style: call with temp == NULL to get the required size in *temp_bytes, then
+ * call again with a device allocation of at least that size.  (In the reference the scratch is
+ * the Pprims-owned uArray work buffers, Pprims.cpp:226-229,332-333.)
+ *
+ * Stable ascending unsigned LSD radix sort of the low sort_bits bits of each key, result left in
+ * `inout`.  sort_bits in [0,32]; the reference's GPU path accepts multiples of 4 (Pprims.cpp:330),
+ * every width is accepted here.  Any n >= 0 (the reference's key-only kernels need n % 256 == 0,
+ * Pprims.cpp:327).  Replaces Pprims::radixSort(device, Buffer<u32>&, n, sortBits), Pprims.cpp:304-406.
+ */
+int b200rs_sort_keys_u32(b200rs_device* dev, uint32_t* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes);
+/* Same on AoS pairs; equal keys keep their input order.  Replaces
+ * Pprims::radixSort(device, Buffer<uint2>&, n, sortBits), Pprims.cpp:200-302. */
+int b200rs_sort_pairs_u32(b200rs_device* dev, b200rs_pair* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes);
+/*
+ * Exclusive prefix sum in u32 arithmetic (wraps mod 2^32): dst[0] = 0, dst[i] = src[0]+...+src[i-1].
+ * dst may equal src.  total_out (device pointer, may be NULL) receives the sum of all n inputs.
+ * Correct for every n (the reference returns without doing anything for n >= 1048576, Pprims.cpp:132-138).
+ * Replaces Pprims::scan(device, dst, src, n, sumOut), Pprims.cpp:122-179.
+ */
+int b200rs_exclusive_scan_u32(b200rs_device* dev, uint32_t* dst, const uint32_t* src, uint64_t n, uint32_t* total_out,
+                              void* temp, size_t* temp_bytes);
+
+/*
+ * HOST-buffer forms: what a caller holding CPU arrays uses in place of the reference's
+ * "getHostPtr / fill / returnHostPtr / radixSort / getHostPtr / read" sequence
+ * (UnitTest/main.cpp:118-139).  Host -> device copy, sort/scan, device -> host copy, stream sync;
+ * device buffers and temp storage are grow-only scratch owned by the handle (like Pprims' work
+ * buffers) and released by b200rs_device_release_scratch / b200rs_device_destroy.
+ * Pinned host memory (b200rs_host_alloc) makes the copies run at full link speed.
+ */
+int b200rs_sort_keys_u32_host(b200rs_device* dev, uint32_t* host_inout, uint64_t n, int sort_bits);
+int b200rs_sort_pairs_u32_host(b200rs_device* dev, b200rs_pair* host_inout, uint64_t n, int sort_bits);
+int b200rs_exclusive_scan_u32_host(b200rs_device* dev, uint32_t* host_dst, const uint32_t* host_src, uint64_t n,
+                                   uint32_t* host_total_out);
+int b200rs_device_release_scratch(b200rs_device* dev);
+
+/* ---- per-launch timing: replaces Device::toggleProfiling, Adl/Adl.h:142 + AdlKernelUtilsCL.inl:654-677 */
+
+typedef struct b200rs_profile_entry {
+    char kernel[48];   /* kernel name, e.g. "onesweep_keys_pass2" */
+    float ms;          /* device time between CUDA events on the handle's stream */
+    uint64_t elements; /* elements the launch processed */
+    uint64_t bytes;    /* algorithmic bytes of the launch */
+} b200rs_profile_entry;
+
+/* While enabled, every kernel the library launches is bracketed by CUDA events. */
+int b200rs_profile_enable(b200rs_device* dev, int enable);
+/* Synchronises the stream, writes up to `capacity` entries recorded since the last read, clears the log. */
+int b200rs_profile_read(b200rs_device* dev, b200rs_profile_entry* out, int capacity, int* count);
+/* Number of kernels launched through this handle since creation (bench.py's gpu_launches). */
+int b200rs_device_launch_count(const b200rs_device* dev, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RS_H */

@@ -1,0 +1,408 @@
+// b200rs_sort.cu -- LSD radix sort of u32 keys / u32-u32 pairs, one scatter pass per 8-bit digit
+// (Onesweep-style) for sm_100a.
+//
+// Replaces the reference's per-4-bit-pass chain StreamCount -> PrefixScan{16,32}PerWi -> SortAndScatter
+// (Tahoe/ClKernels/RadixSort32Kernels.cl:178-631, RadixSortKeyValueKernels.cl:184-663, driven by
+// Pprims::radixSort, Pprims.cpp:200-406): 8 passes x 3 launches and 96 B/key there; here
+//   1 launch  digit_histogram_kernel : reads the input once, builds the histograms of ALL digits
+//   P launches onesweep_kernel       : P = ceil(sort_bits/8); reads each element once, writes it once
+// => 4 + 8P bytes per key (36 B at 32 bits), 8 + 16P per pair.
+//
+// onesweep_kernel, per tile of TILE consecutive elements (tile ids from an atomic ticket):
+//   1. warp-striped load: warp w owns a contiguous slice, element (i, lane) sits at slice + i*32 + lane,
+//      so (i, lane) order == input order -- this is what makes the ranking stable;
+//   2. warp multisplit ranking: __match_any_sync groups the lanes holding the same digit; the lowest
+//      lane of each group bumps that warp's private counter in shared memory; rank = old counter +
+//      number of lower lanes in the group (no atomics, 32-lane warps);
+//   3. per-digit totals across warps -> published to the look-back table as PARTIAL; tile-local bin
+//      starts by a 256-wide block scan; elements scattered to their tile-local sorted slot in shared memory;
+//   4. decoupled look-back, one thread per digit: sums predecessors' PARTIALs until an INCLUSIVE is met,
+//      publishes its own INCLUSIVE; tile 0 seeds the chain with the exclusive scan of the global histogram,
+//      so there is no separate scan launch;
+//   5. the tile is written out from shared memory in sorted order: consecutive threads write consecutive
+//      addresses within each digit's run.
+// Look-back words are 64-bit {tag:8 | count:56}; tag = 2*pass + {1 PARTIAL, 2 INCLUSIVE}, so one table,
+// zeroed once per sort, serves every pass and counts never overflow (n up to 2^56).
+#include "b200rs_internal.h"
+
+namespace {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int MAX_PASSES = 4;
+
+// ---- element traits: u32 key, or the 8-byte AoS pair {key, value} (Tahoe::uint2, Math.h:175-188) ----
+template <typename ElemT> struct Elem;
+template <> struct Elem<uint32_t> {
+    static __device__ __forceinline__ uint32_t key(uint32_t e) { return e; }
+};
+template <> struct Elem<uint2> {
+    static __device__ __forceinline__ uint32_t key(uint2 e) { return e.x; }
+};
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// =================================================================================================
+// Histogram of every digit in one read of the input.
+// =================================================================================================
+constexpr int HIST_THREADS = 512;
+constexpr int HIST_VEC_PER_THREAD = 4;  // uint4 loads in flight per thread
+
+template <typename ElemT>
+__global__ void __launch_bounds__(HIST_THREADS)
+digit_histogram_kernel(const ElemT* __restrict__ in, uint64_t n, int num_passes, uint32_t key_mask,
+                       unsigned long long* __restrict__ ghist /*[num_passes][RADIX]*/) {
+    __shared__ uint32_t s_hist[MAX_PASSES][RADIX];
+    for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += HIST_THREADS) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+
+    constexpr int KEYS_PER_VEC = 16 / sizeof(ElemT);  // 4 keys or 2 pairs per uint4
+    const uint64_t nvec = n / KEYS_PER_VEC;
+    const uint4* in4 = reinterpret_cast<const uint4*>(in);
+
+    auto count = [&](uint32_t key) {
+        key &= key_mask;
+#pragma unroll
+        for (int p = 0; p < MAX_PASSES; ++p)
+            if (p < num_passes) atomicAdd(&s_hist[p][(key >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+    };
+
+    const uint64_t stride = (uint64_t)gridDim.x * HIST_THREADS;
+    uint64_t v = (uint64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
+    // main loop: HIST_VEC_PER_THREAD independent 16-byte loads per thread before any use
+    for (; v + (HIST_VEC_PER_THREAD - 1) * stride < nvec; v += HIST_VEC_PER_THREAD * stride) {
+        uint4 q[HIST_VEC_PER_THREAD];
+#pragma unroll
+        for (int u = 0; u < HIST_VEC_PER_THREAD; ++u) q[u] = __ldg(in4 + v + u * stride);
+#pragma unroll
+        for (int u = 0; u < HIST_VEC_PER_THREAD; ++u) {
+            if (sizeof(ElemT) == 4) { count(q[u].x); count(q[u].y); count(q[u].z); count(q[u].w); }
+            else                    { count(q[u].x); count(q[u].z); }
+        }
+    }
+    for (; v < nvec; v += stride) {
+        const uint4 q = __ldg(in4 + v);
+        if (sizeof(ElemT) == 4) { count(q.x); count(q.y); count(q.z); count(q.w); }
+        else                    { count(q.x); count(q.z); }
+    }
+    // ragged tail (n not a multiple of the vector width): block 0 only
+    if (blockIdx.x == 0) {
+        const uint64_t i = nvec * KEYS_PER_VEC + threadIdx.x;
+        if (i < n) count(Elem<ElemT>::key(in[i]));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < num_passes * RADIX; i += HIST_THREADS) {
+        const uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(&ghist[i], (unsigned long long)c);
+    }
+}
+
+// Same, for inputs whose base pointer is not 16-byte aligned (element-wise loads).
+template <typename ElemT>
+__global__ void __launch_bounds__(HIST_THREADS)
+digit_histogram_unaligned_kernel(const ElemT* __restrict__ in, uint64_t n, int num_passes, uint32_t key_mask,
+                                 unsigned long long* __restrict__ ghist) {
+    __shared__ uint32_t s_hist[MAX_PASSES][RADIX];
+    for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += HIST_THREADS) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * HIST_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * HIST_THREADS + threadIdx.x; i < n; i += stride) {
+        const uint32_t key = Elem<ElemT>::key(in[i]) & key_mask;
+#pragma unroll
+        for (int p = 0; p < MAX_PASSES; ++p)
+            if (p < num_passes) atomicAdd(&s_hist[p][(key >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < num_passes * RADIX; i += HIST_THREADS) {
+        const uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(&ghist[i], (unsigned long long)c);
+    }
+}
+
+// =================================================================================================
+// One scatter pass.
+// =================================================================================================
+constexpr uint64_t LB_VALUE_MASK = (1ull << 56) - 1;
+constexpr int LB_TAG_SHIFT = 56;
+
+template <typename ElemT, int THREADS, int IPT>
+struct OnesweepConfig {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * IPT;
+    static constexpr int WARP_SLICE = 32 * IPT;
+    struct Smem {
+        ElemT staged[TILE];                 // tile in tile-local sorted order
+        uint32_t warp_count[WARPS][RADIX];  // per-warp digit counters, then exclusive-over-warps offsets
+        uint64_t global_delta[RADIX];       // (global start of this tile's run of digit d) - (tile-local start)
+        uint32_t bin_start[RADIX];          // tile-local exclusive start of each digit
+        uint32_t scan_warp_total[RADIX / 32];
+        uint32_t tile;
+    };
+};
+
+// 256-wide exclusive scan by threads 0..255 (8 warps); every one of those threads must call it.
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan_256(T x, T* warp_totals /*[8] shared*/, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    T inc = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += y;
+    }
+    if (lane == 31) warp_totals[warp] = inc;
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // named barrier: only the 256 digit threads
+    T base = 0;
+#pragma unroll
+    for (int w = 0; w < RADIX / 32; ++w)
+        if (w < warp) base += warp_totals[w];
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // warp_totals may be reused by the caller
+    return base + inc - x;
+}
+
+template <typename ElemT, int THREADS, int IPT>
+__global__ void __launch_bounds__(THREADS)
+onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
+                const unsigned long long* __restrict__ ghist_pass /*[RADIX]*/, uint64_t* lookback /*[tiles][RADIX]*/,
+                uint32_t* ticket, uint32_t tag_base) {
+    using Cfg = OnesweepConfig<ElemT, THREADS, IPT>;
+    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t TAG_PARTIAL = (uint64_t)(tag_base + 1) << LB_TAG_SHIFT;
+    const uint64_t TAG_INCLUSIVE = (uint64_t)(tag_base + 2) << LB_TAG_SHIFT;
+
+    if (tid == 0) s.tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int i = tid; i < Cfg::WARPS * RADIX; i += THREADS) (&s.warp_count[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s.tile;
+    const uint64_t tile_base = (uint64_t)tile * Cfg::TILE;
+    const uint32_t valid = (uint32_t)min((uint64_t)Cfg::TILE, n - tile_base);  // elements of this tile that exist
+    const bool full = valid == Cfg::TILE;
+
+    // ---- 1. warp-striped load ----
+    ElemT elem[IPT];
+    uint32_t digit[IPT];
+    const uint32_t slice = warp * Cfg::WARP_SLICE + lane;  // tile-local index of item 0
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) elem[i] = in[tile_base + slice + i * 32];
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) digit[i] = (Elem<ElemT>::key(elem[i]) >> shift) & digit_mask;
+    } else {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const uint32_t local = slice + i * 32;
+            if (local < valid) {
+                elem[i] = in[tile_base + local];
+                digit[i] = (Elem<ElemT>::key(elem[i]) >> shift) & digit_mask;
+            } else {
+                digit[i] = RADIX - 1;  // padding: ranks behind every real element of the last bin, never written
+            }
+        }
+    }
+
+    // ---- 2. warp multisplit ranking ----
+    uint32_t rank[IPT];
+    uint32_t* my_count = s.warp_count[warp];
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit[i]);
+        const uint32_t lower = peers & lt;
+        uint32_t before = 0;
+        if (lower == 0) {  // lowest lane of the group owns the counter update
+            before = my_count[digit[i]];
+            my_count[digit[i]] = before + __popc(peers);
+        }
+        __syncwarp();
+        before = __shfl_sync(0xffffffffu, before, __ffs(peers) - 1);
+        rank[i] = before + __popc(lower);
+    }
+    __syncthreads();
+
+    // ---- 3. per-digit totals, tile-local bin starts ----
+    uint32_t total = 0;
+    if (tid < RADIX) {
+#pragma unroll
+        for (int w = 0; w < Cfg::WARPS; ++w) {
+            const uint32_t c = s.warp_count[w][tid];
+            s.warp_count[w][tid] = total;
+            total += c;
+        }
+        const uint32_t start = block_exclusive_scan_256<uint32_t>(total, s.scan_warp_total, tid);
+        s.bin_start[tid] = start;
+        if (tid == RADIX - 1) total -= Cfg::TILE - valid;  // padding is not data
+        if (tile != 0) st_relaxed_u64(&lookback[(uint64_t)tile * RADIX + tid], TAG_PARTIAL | total);
+    }
+    __syncthreads();
+
+    // scatter into tile-local sorted order
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const uint32_t pos = s.bin_start[digit[i]] + my_count[digit[i]] + rank[i];
+        if (full || pos < valid) s.staged[pos] = elem[i];
+    }
+
+    // ---- 4. decoupled look-back, one thread per digit ----
+    if (tid < RADIX) {
+        uint64_t exclusive;
+        if (tile == 0) {
+            // seed: global start of each digit = exclusive scan of the whole-input histogram
+            uint64_t* scratch = reinterpret_cast<uint64_t*>(s.global_delta);  // 8 x u64 fits, not yet in use
+            exclusive = block_exclusive_scan_256<uint64_t>((uint64_t)ghist_pass[tid], scratch, tid);
+        } else {
+            exclusive = 0;
+            int64_t t = (int64_t)tile - 1;
+            while (true) {
+                const uint64_t w = ld_relaxed_u64(&lookback[(uint64_t)t * RADIX + tid]);
+                const uint64_t tag = w & ~LB_VALUE_MASK;
+                if (tag == TAG_INCLUSIVE) {
+                    exclusive += w & LB_VALUE_MASK;
+                    break;
+                }
+                if (tag == TAG_PARTIAL) {
+                    exclusive += w & LB_VALUE_MASK;
+                    --t;  // tile 0 always publishes INCLUSIVE, so t never goes negative
+                }
+                // anything else: not published yet for this pass -> poll again
+            }
+        }
+        st_relaxed_u64(&lookback[(uint64_t)tile * RADIX + tid], TAG_INCLUSIVE | (exclusive + total));
+        s.global_delta[tid] = exclusive - s.bin_start[tid];
+    }
+    __syncthreads();
+
+    // ---- 5. write the tile out in sorted order ----
+#pragma unroll 4
+    for (uint32_t j = tid; j < valid; j += THREADS) {
+        const ElemT e = s.staged[j];
+        const uint32_t d = (Elem<ElemT>::key(e) >> shift) & digit_mask;
+        out[s.global_delta[d] + j] = e;
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+
+template <typename ElemT> struct Tuning;
+template <> struct Tuning<uint32_t> { static constexpr int THREADS = 512, IPT = 16; };
+template <> struct Tuning<uint2>    { static constexpr int THREADS = 512, IPT = 8; };
+
+struct SortPlan {
+    int passes;
+    uint32_t num_tiles;
+    size_t alt_off, hist_off, ticket_off, lookback_off, total_bytes;
+    size_t clear_off, clear_bytes;  // histograms + tickets + look-back table are zeroed per call
+};
+
+template <typename ElemT>
+int make_plan(uint64_t n, int sort_bits, SortPlan* p) {
+    using T = Tuning<ElemT>;
+    constexpr uint64_t TILE = (uint64_t)T::THREADS * T::IPT;
+    if (sort_bits < 0 || sort_bits > 32) return B200RS_ERR_INVALID_ARGUMENT;
+    const uint64_t tiles = (n + TILE - 1) / TILE;
+    if (tiles > 0x7fffffffull) return B200RS_ERR_TOO_LARGE;
+    p->passes = (sort_bits + RADIX_BITS - 1) / RADIX_BITS;
+    p->num_tiles = (uint32_t)tiles;
+    size_t off = 0;
+    p->alt_off = off;      off += b200rs_align_up((size_t)n * sizeof(ElemT), 256);
+    p->clear_off = off;
+    p->hist_off = off;     off += b200rs_align_up(sizeof(unsigned long long) * MAX_PASSES * RADIX, 256);
+    p->ticket_off = off;   off += 256;
+    p->lookback_off = off; off += b200rs_align_up((size_t)tiles * RADIX * sizeof(uint64_t), 256);
+    p->clear_bytes = off - p->clear_off;
+    p->total_bytes = off ? off : 256;
+    return B200RS_OK;
+}
+
+template <typename ElemT>
+int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes, const char* what) {
+    using T = Tuning<ElemT>;
+    using Cfg = OnesweepConfig<ElemT, T::THREADS, T::IPT>;
+    if (!dev || !temp_bytes) return B200RS_ERR_INVALID_ARGUMENT;
+    SortPlan plan;
+    B200RS_TRY(make_plan<ElemT>(n, sort_bits, &plan));
+    if (!temp) {
+        *temp_bytes = plan.total_bytes;
+        return B200RS_OK;
+    }
+    if (*temp_bytes < plan.total_bytes) return B200RS_ERR_TEMP_TOO_SMALL;
+    if (n && !inout) return B200RS_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)inout & (sizeof(ElemT) - 1)) || ((uintptr_t)temp & 255u)) return B200RS_ERR_INVALID_ARGUMENT;
+    if (n <= 1 || plan.passes == 0) return B200RS_OK;  // nothing to order
+
+    b200rs_device_guard guard(dev);
+    char* base = static_cast<char*>(temp);
+    ElemT* alt = reinterpret_cast<ElemT*>(base + plan.alt_off);
+    unsigned long long* ghist = reinterpret_cast<unsigned long long*>(base + plan.hist_off);
+    uint32_t* tickets = reinterpret_cast<uint32_t*>(base + plan.ticket_off);
+    uint64_t* lookback = reinterpret_cast<uint64_t*>(base + plan.lookback_off);
+    B200RS_CUDA(cudaMemsetAsync(base + plan.clear_off, 0, plan.clear_bytes, dev->stream));
+
+    const uint32_t key_mask = sort_bits == 32 ? 0xffffffffu : ((1u << sort_bits) - 1u);
+    char label[48];
+    {
+        snprintf(label, sizeof(label), "digit_histogram_%s", what);
+        b200rs_launch_scope scope(dev, label, n, n * sizeof(ElemT));
+        const uint64_t per_block = (uint64_t)HIST_THREADS * HIST_VEC_PER_THREAD * (16 / sizeof(ElemT));
+        uint64_t blocks = (n + per_block - 1) / per_block;
+        const uint64_t max_blocks = (uint64_t)dev->num_sms * 4;  // 4 x 512 threads per SM, grid-stride beyond that
+        if (blocks > max_blocks) blocks = max_blocks;
+        if (((uintptr_t)inout & 15u) == 0)
+            digit_histogram_kernel<ElemT><<<(unsigned)blocks, HIST_THREADS, 0, dev->stream>>>(inout, n, plan.passes, key_mask, ghist);
+        else
+            digit_histogram_unaligned_kernel<ElemT><<<(unsigned)blocks, HIST_THREADS, 0, dev->stream>>>(inout, n, plan.passes, key_mask, ghist);
+    }
+    B200RS_CUDA(cudaGetLastError());
+
+    auto kernel = onesweep_kernel<ElemT, T::THREADS, T::IPT>;
+    const size_t smem = sizeof(typename Cfg::Smem);
+    static bool attr_set[64] = {false};
+    if (!attr_set[dev->device_idx & 63]) {
+        B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev->device_idx & 63] = true;
+    }
+    ElemT* src = inout;
+    ElemT* dst = alt;
+    for (int p = 0; p < plan.passes; ++p) {
+        const int shift = p * RADIX_BITS;
+        const int width = sort_bits - shift < RADIX_BITS ? sort_bits - shift : RADIX_BITS;
+        const uint32_t digit_mask = (1u << width) - 1u;
+        snprintf(label, sizeof(label), "onesweep_%s_pass%d", what, p);
+        {
+            b200rs_launch_scope scope(dev, label, n, 2ull * n * sizeof(ElemT));
+            kernel<<<plan.num_tiles, T::THREADS, smem, dev->stream>>>(src, dst, n, shift, digit_mask, ghist + (size_t)p * RADIX, lookback,
+                                                                      tickets + p, (uint32_t)(2 * p));
+        }
+        B200RS_CUDA(cudaGetLastError());
+        ElemT* t = src; src = dst; dst = t;
+    }
+    // odd pass count: the result sits in the alternate buffer (the reference copies back too, Pprims.cpp:400-403)
+    if (src != inout) B200RS_CUDA(cudaMemcpyAsync(inout, src, (size_t)n * sizeof(ElemT), cudaMemcpyDeviceToDevice, dev->stream));
+    return B200RS_OK;
+}
+
+}  // namespace
+
+extern "C" int b200rs_sort_keys_u32(b200rs_device* dev, uint32_t* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes) {
+    return sort_impl<uint32_t>(dev, inout, n, sort_bits, temp, temp_bytes, "keys");
+}
+
+extern "C" int b200rs_sort_pairs_u32(b200rs_device* dev, b200rs_pair* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes) {
+    return sort_impl<uint2>(dev, reinterpret_cast<uint2*>(inout), n, sort_bits, temp, temp_bytes, "pairs");
+}
