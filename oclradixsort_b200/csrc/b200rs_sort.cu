@@ -137,16 +137,39 @@ digit_histogram_unaligned_kernel(const ElemT* __restrict__ in, uint64_t n, int n
 constexpr uint64_t LB_VALUE_MASK = (1ull << 56) - 1;
 constexpr int LB_TAG_SHIFT = 56;
 
+// How the lanes of a warp that hold the same digit find each other.
+//   RANK_BALLOT : 8 x vote.ballot (one per digit bit), no shared memory.  Measured 13.8 SM-cycles per 32 keys.
+//   RANK_MATCH  : __match_any_sync (MATCH.ANY).  Measured 62 SM-cycles per 32 keys on B200 (about 2 cycles per
+//                 distinct value in the warp) -- kept only so the measurement can be reproduced.
+enum RankMode { RANK_BALLOT = 0, RANK_MATCH = 1 };
+
+template <int MODE>
+__device__ __forceinline__ uint32_t same_digit_lanes(uint32_t digit) {
+    if (MODE == RANK_MATCH) return __match_any_sync(0xffffffffu, digit);
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < RADIX_BITS; ++k) {
+        uint32_t b;  // lanes whose bit k equals mine
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+            "and.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t@!p not.b32 %0, %0;\n\t}"
+            : "=r"(b)
+            : "r"(digit), "r"(1u << k));
+        peers &= b;
+    }
+    return peers;
+}
+
 template <typename ElemT, int THREADS, int IPT>
 struct OnesweepConfig {
     static constexpr int WARPS = THREADS / 32;
     static constexpr int TILE = THREADS * IPT;
     static constexpr int WARP_SLICE = 32 * IPT;
     struct Smem {
-        ElemT staged[TILE];                 // tile in tile-local sorted order
-        uint32_t warp_count[WARPS][RADIX];  // per-warp digit counters, then exclusive-over-warps offsets
-        uint64_t global_delta[RADIX];       // (global start of this tile's run of digit d) - (tile-local start)
-        uint32_t bin_start[RADIX];          // tile-local exclusive start of each digit
+        ElemT staged[TILE];                  // tile in tile-local sorted order
+        uint32_t warp_offset[WARPS][RADIX];  // per-warp digit counts -> running tile-local slot of (warp, digit)
+        uint64_t global_delta[RADIX];        // (global start of this tile's run of digit d) - (tile-local start)
         uint32_t scan_warp_total[RADIX / 32];
         uint32_t tile;
     };
@@ -172,7 +195,7 @@ __device__ __forceinline__ T block_exclusive_scan_256(T x, T* warp_totals /*[8] 
     return base + inc - x;
 }
 
-template <typename ElemT, int THREADS, int IPT>
+template <typename ElemT, int THREADS, int IPT, int MODE>
 __global__ void __launch_bounds__(THREADS)
 onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
                 const unsigned long long* __restrict__ ghist_pass /*[RADIX]*/, uint64_t* lookback /*[tiles][RADIX]*/,
@@ -188,75 +211,64 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
 
     if (tid == 0) s.tile = atomicAdd(ticket, 1u);
 #pragma unroll
-    for (int i = tid; i < Cfg::WARPS * RADIX; i += THREADS) (&s.warp_count[0][0])[i] = 0;
+    for (int i = tid; i < Cfg::WARPS * RADIX; i += THREADS) (&s.warp_offset[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s.tile;
     const uint64_t tile_base = (uint64_t)tile * Cfg::TILE;
     const uint32_t valid = (uint32_t)min((uint64_t)Cfg::TILE, n - tile_base);  // elements of this tile that exist
     const bool full = valid == Cfg::TILE;
 
-    // ---- 1. warp-striped load ----
+    // ---- 1. warp-striped load + per-warp digit counts (shared-memory reductions, no return value) ----
     ElemT elem[IPT];
-    uint32_t digit[IPT];
+    uint32_t* my_offset = s.warp_offset[warp];
     const uint32_t slice = warp * Cfg::WARP_SLICE + lane;  // tile-local index of item 0
     if (full) {
 #pragma unroll
         for (int i = 0; i < IPT; ++i) elem[i] = in[tile_base + slice + i * 32];
 #pragma unroll
-        for (int i = 0; i < IPT; ++i) digit[i] = (Elem<ElemT>::key(elem[i]) >> shift) & digit_mask;
+        for (int i = 0; i < IPT; ++i) atomicAdd(&my_offset[(Elem<ElemT>::key(elem[i]) >> shift) & digit_mask], 1u);
     } else {
 #pragma unroll
         for (int i = 0; i < IPT; ++i) {
             const uint32_t local = slice + i * 32;
             if (local < valid) {
                 elem[i] = in[tile_base + local];
-                digit[i] = (Elem<ElemT>::key(elem[i]) >> shift) & digit_mask;
-            } else {
-                digit[i] = RADIX - 1;  // padding: ranks behind every real element of the last bin, never written
+                atomicAdd(&my_offset[(Elem<ElemT>::key(elem[i]) >> shift) & digit_mask], 1u);
             }
         }
     }
+    __syncthreads();
 
-    // ---- 2. warp multisplit ranking ----
-    uint32_t rank[IPT];
-    uint32_t* my_count = s.warp_count[warp];
+    // ---- 2. one thread per digit: totals -> PARTIAL published early; tile-local slots for every (warp, digit) ----
+    uint32_t total = 0, bin_start = 0;
+    if (tid < RADIX) {
+#pragma unroll
+        for (int w = 0; w < Cfg::WARPS; ++w) total += s.warp_offset[w][tid];
+        if (tile != 0) st_relaxed_u64(&lookback[(uint64_t)tile * RADIX + tid], TAG_PARTIAL | total);
+        bin_start = block_exclusive_scan_256<uint32_t>(total, s.scan_warp_total, tid);
+        uint32_t run = bin_start;
+#pragma unroll
+        for (int w = 0; w < Cfg::WARPS; ++w) {
+            const uint32_t c = s.warp_offset[w][tid];
+            s.warp_offset[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. warp multisplit ranking; each element goes straight to its tile-local sorted slot ----
     const uint32_t lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-        const uint32_t peers = __match_any_sync(0xffffffffu, digit[i]);
+        const bool live = full || (slice + i * 32 < valid);
+        const uint32_t digit = live ? ((Elem<ElemT>::key(elem[i]) >> shift) & digit_mask) : (uint32_t)(RADIX - 1);
+        uint32_t peers = same_digit_lanes<MODE>(digit);
+        if (!full) peers &= __ballot_sync(0xffffffffu, live);  // padding lanes are nobody's peers
         const uint32_t lower = peers & lt;
-        uint32_t before = 0;
-        if (lower == 0) {  // lowest lane of the group owns the counter update
-            before = my_count[digit[i]];
-            my_count[digit[i]] = before + __popc(peers);
-        }
-        __syncwarp();
-        before = __shfl_sync(0xffffffffu, before, __ffs(peers) - 1);
-        rank[i] = before + __popc(lower);
-    }
-    __syncthreads();
-
-    // ---- 3. per-digit totals, tile-local bin starts ----
-    uint32_t total = 0;
-    if (tid < RADIX) {
-#pragma unroll
-        for (int w = 0; w < Cfg::WARPS; ++w) {
-            const uint32_t c = s.warp_count[w][tid];
-            s.warp_count[w][tid] = total;
-            total += c;
-        }
-        const uint32_t start = block_exclusive_scan_256<uint32_t>(total, s.scan_warp_total, tid);
-        s.bin_start[tid] = start;
-        if (tid == RADIX - 1) total -= Cfg::TILE - valid;  // padding is not data
-        if (tile != 0) st_relaxed_u64(&lookback[(uint64_t)tile * RADIX + tid], TAG_PARTIAL | total);
-    }
-    __syncthreads();
-
-    // scatter into tile-local sorted order
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        const uint32_t pos = s.bin_start[digit[i]] + my_count[digit[i]] + rank[i];
-        if (full || pos < valid) s.staged[pos] = elem[i];
+        uint32_t slot = 0;
+        if (live && lower == 0) slot = atomicAdd(&my_offset[digit], (uint32_t)__popc(peers));  // lowest lane of the group
+        slot = __shfl_sync(0xffffffffu, slot, __ffs(peers | (live ? 0u : (1u << lane))) - 1);
+        if (live) s.staged[slot + __popc(lower)] = elem[i];
     }
 
     // ---- 4. decoupled look-back, one thread per digit ----
@@ -264,7 +276,7 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
         uint64_t exclusive;
         if (tile == 0) {
             // seed: global start of each digit = exclusive scan of the whole-input histogram
-            uint64_t* scratch = reinterpret_cast<uint64_t*>(s.global_delta);  // 8 x u64 fits, not yet in use
+            uint64_t* scratch = s.global_delta;  // 8 x u64 of it, not yet in use
             exclusive = block_exclusive_scan_256<uint64_t>((uint64_t)ghist_pass[tid], scratch, tid);
         } else {
             exclusive = 0;
@@ -284,7 +296,7 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
             }
         }
         st_relaxed_u64(&lookback[(uint64_t)tile * RADIX + tid], TAG_INCLUSIVE | (exclusive + total));
-        s.global_delta[tid] = exclusive - s.bin_start[tid];
+        s.global_delta[tid] = exclusive - bin_start;
     }
     __syncthreads();
 
@@ -299,26 +311,69 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
 
 // ---- host side -------------------------------------------------------------------------------------
 
-template <typename ElemT> struct Tuning;
-template <> struct Tuning<uint32_t> { static constexpr int THREADS = 512, IPT = 16; };
-template <> struct Tuning<uint2>    { static constexpr int THREADS = 512, IPT = 8; };
+// Compiled variants; index chosen by B200RS_KEYS_VARIANT / B200RS_PAIRS_VARIANT (development knob), default 0.
+struct Variant {
+    const void* kernel;
+    int threads, ipt;
+    size_t smem;
+    const char* name;
+};
+#define B200RS_VARIANT(ElemT, THREADS, IPT, MODE) \
+    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE}
+
+template <typename ElemT> struct Variants;
+template <> struct Variants<uint32_t> {
+    static const Variant* list(int* count) {
+        static const Variant v[] = {
+            B200RS_VARIANT(uint32_t, 512, 16, RANK_BALLOT),
+            B200RS_VARIANT(uint32_t, 512, 16, RANK_MATCH),
+            B200RS_VARIANT(uint32_t, 256, 16, RANK_BALLOT),
+            B200RS_VARIANT(uint32_t, 512, 12, RANK_BALLOT),
+            B200RS_VARIANT(uint32_t, 512, 20, RANK_BALLOT),
+            B200RS_VARIANT(uint32_t, 1024, 8, RANK_BALLOT),
+        };
+        *count = sizeof(v) / sizeof(v[0]);
+        return v;
+    }
+    static const char* env() { return "B200RS_KEYS_VARIANT"; }
+};
+template <> struct Variants<uint2> {
+    static const Variant* list(int* count) {
+        static const Variant v[] = {
+            B200RS_VARIANT(uint2, 512, 16, RANK_BALLOT),
+            B200RS_VARIANT(uint2, 512, 8, RANK_BALLOT),
+            B200RS_VARIANT(uint2, 256, 16, RANK_BALLOT),
+            B200RS_VARIANT(uint2, 512, 12, RANK_BALLOT),
+        };
+        *count = sizeof(v) / sizeof(v[0]);
+        return v;
+    }
+    static const char* env() { return "B200RS_PAIRS_VARIANT"; }
+};
+constexpr uint64_t MIN_TILE = 256 * 16;  // smallest tile among the variants: temp storage is sized for it
+
+template <typename ElemT>
+const Variant& pick_variant() {
+    int count = 0;
+    const Variant* v = Variants<ElemT>::list(&count);
+    const char* e = getenv(Variants<ElemT>::env());
+    int idx = e ? atoi(e) : 0;
+    if (idx < 0 || idx >= count) idx = 0;
+    return v[idx];
+}
 
 struct SortPlan {
     int passes;
-    uint32_t num_tiles;
     size_t alt_off, hist_off, ticket_off, lookback_off, total_bytes;
     size_t clear_off, clear_bytes;  // histograms + tickets + look-back table are zeroed per call
 };
 
 template <typename ElemT>
 int make_plan(uint64_t n, int sort_bits, SortPlan* p) {
-    using T = Tuning<ElemT>;
-    constexpr uint64_t TILE = (uint64_t)T::THREADS * T::IPT;
     if (sort_bits < 0 || sort_bits > 32) return B200RS_ERR_INVALID_ARGUMENT;
-    const uint64_t tiles = (n + TILE - 1) / TILE;
+    const uint64_t tiles = (n + MIN_TILE - 1) / MIN_TILE;
     if (tiles > 0x7fffffffull) return B200RS_ERR_TOO_LARGE;
     p->passes = (sort_bits + RADIX_BITS - 1) / RADIX_BITS;
-    p->num_tiles = (uint32_t)tiles;
     size_t off = 0;
     p->alt_off = off;      off += b200rs_align_up((size_t)n * sizeof(ElemT), 256);
     p->clear_off = off;
@@ -332,8 +387,6 @@ int make_plan(uint64_t n, int sort_bits, SortPlan* p) {
 
 template <typename ElemT>
 int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes, const char* what) {
-    using T = Tuning<ElemT>;
-    using Cfg = OnesweepConfig<ElemT, T::THREADS, T::IPT>;
     if (!dev || !temp_bytes) return B200RS_ERR_INVALID_ARGUMENT;
     SortPlan plan;
     B200RS_TRY(make_plan<ElemT>(n, sort_bits, &plan));
@@ -347,12 +400,17 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     if (n <= 1 || plan.passes == 0) return B200RS_OK;  // nothing to order
 
     b200rs_device_guard guard(dev);
+    const Variant& var = pick_variant<ElemT>();
+    const uint64_t tile_elems = (uint64_t)var.threads * var.ipt;
+    const uint32_t num_tiles = (uint32_t)((n + tile_elems - 1) / tile_elems);
     char* base = static_cast<char*>(temp);
     ElemT* alt = reinterpret_cast<ElemT*>(base + plan.alt_off);
     unsigned long long* ghist = reinterpret_cast<unsigned long long*>(base + plan.hist_off);
     uint32_t* tickets = reinterpret_cast<uint32_t*>(base + plan.ticket_off);
     uint64_t* lookback = reinterpret_cast<uint64_t*>(base + plan.lookback_off);
-    B200RS_CUDA(cudaMemsetAsync(base + plan.clear_off, 0, plan.clear_bytes, dev->stream));
+    // zero the histograms, the tickets and the part of the look-back table this tiling uses
+    const size_t clear_bytes = (plan.lookback_off - plan.clear_off) + (size_t)num_tiles * RADIX * sizeof(uint64_t);
+    B200RS_CUDA(cudaMemsetAsync(base + plan.clear_off, 0, clear_bytes, dev->stream));
 
     const uint32_t key_mask = sort_bits == 32 ? 0xffffffffu : ((1u << sort_bits) - 1u);
     char label[48];
@@ -370,26 +428,23 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     }
     B200RS_CUDA(cudaGetLastError());
 
-    auto kernel = onesweep_kernel<ElemT, T::THREADS, T::IPT>;
-    const size_t smem = sizeof(typename Cfg::Smem);
-    static bool attr_set[64] = {false};
-    if (!attr_set[dev->device_idx & 63]) {
-        B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[dev->device_idx & 63] = true;
-    }
+    B200RS_CUDA(cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
     ElemT* src = inout;
     ElemT* dst = alt;
     for (int p = 0; p < plan.passes; ++p) {
-        const int shift = p * RADIX_BITS;
+        int shift = p * RADIX_BITS;
         const int width = sort_bits - shift < RADIX_BITS ? sort_bits - shift : RADIX_BITS;
-        const uint32_t digit_mask = (1u << width) - 1u;
+        uint32_t digit_mask = (1u << width) - 1u;
+        const unsigned long long* ghist_pass = ghist + (size_t)p * RADIX;
+        uint32_t* ticket = tickets + p;
+        uint32_t tag_base = (uint32_t)(2 * p);
+        uint64_t n_arg = n;
+        void* args[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lookback, &ticket, &tag_base};
         snprintf(label, sizeof(label), "onesweep_%s_pass%d", what, p);
         {
             b200rs_launch_scope scope(dev, label, n, 2ull * n * sizeof(ElemT));
-            kernel<<<plan.num_tiles, T::THREADS, smem, dev->stream>>>(src, dst, n, shift, digit_mask, ghist + (size_t)p * RADIX, lookback,
-                                                                      tickets + p, (uint32_t)(2 * p));
+            B200RS_CUDA(cudaLaunchKernel(var.kernel, dim3(num_tiles), dim3(var.threads), args, var.smem, dev->stream));
         }
-        B200RS_CUDA(cudaGetLastError());
         ElemT* t = src; src = dst; dst = t;
     }
     // odd pass count: the result sits in the alternate buffer (the reference copies back too, Pprims.cpp:400-403)
