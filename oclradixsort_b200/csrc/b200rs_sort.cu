@@ -141,7 +141,11 @@ constexpr int LB_TAG_SHIFT = 56;
 //   RANK_BALLOT : 8 x vote.ballot (one per digit bit), no shared memory.  Measured 13.8 SM-cycles per 32 keys.
 //   RANK_MATCH  : __match_any_sync (MATCH.ANY).  Measured 62 SM-cycles per 32 keys on B200 (about 2 cycles per
 //                 distinct value in the warp) -- kept only so the measurement can be reproduced.
-enum RankMode { RANK_BALLOT = 0, RANK_MATCH = 1 };
+//   RANK_ATOMIC_UNORDERED : EXPERIMENT, NOT SELECTABLE BY DEFAULT.  One shared-memory atomicAdd per key and no
+//                 peer search: 3.5 SM-cycles per 32 keys, but the order of same-digit lanes inside one warp
+//                 instruction is whatever the hardware does (undocumented), so stability is not guaranteed.
+//                 Exists to measure what the guaranteed ranking costs.
+enum RankMode { RANK_BALLOT = 0, RANK_MATCH = 1, RANK_ATOMIC_UNORDERED = 2 };
 
 template <int MODE>
 __device__ __forceinline__ uint32_t same_digit_lanes(uint32_t digit) {
@@ -159,6 +163,26 @@ __device__ __forceinline__ uint32_t same_digit_lanes(uint32_t digit) {
         peers &= b;
     }
     return peers;
+}
+
+__device__ __forceinline__ uint32_t lanemask_gt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
+    return m;
+}
+// shared-memory accesses through 32-bit shared-window addresses (keeps address arithmetic to one LEA)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void red_add_shared(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_shared(uint32_t addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void st_shared(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_shared(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
 template <typename ElemT, int THREADS, int IPT>
@@ -195,56 +219,53 @@ __device__ __forceinline__ T block_exclusive_scan_256(T x, T* warp_totals /*[8] 
     return base + inc - x;
 }
 
-template <typename ElemT, int THREADS, int IPT, int MODE>
-__global__ void __launch_bounds__(THREADS)
-onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
-                const unsigned long long* __restrict__ ghist_pass /*[RADIX]*/, uint64_t* lookback /*[tiles][RADIX]*/,
-                uint32_t* ticket, uint32_t tag_base) {
+// digit of a key: byte `shift/8` (PRMT) when the pass is a whole byte, shift-and-mask otherwise
+template <bool BYTE_DIGIT>
+__device__ __forceinline__ uint32_t digit_of(uint32_t key, int shift, uint32_t digit_mask, uint32_t prmt_sel) {
+    if (BYTE_DIGIT) return __byte_perm(key, 0u, prmt_sel);
+    return (key >> shift) & digit_mask;
+}
+// Same value, but opaque to the optimiser: used in the counting phase so the digits are recomputed (one PRMT)
+// in the ranking phase instead of being kept alive in IPT extra registers across two barriers.
+template <bool BYTE_DIGIT>
+__device__ __forceinline__ uint32_t digit_of_opaque(uint32_t key, int shift, uint32_t digit_mask, uint32_t prmt_sel) {
+    uint32_t d;
+    if (BYTE_DIGIT) {
+        asm volatile("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(key), "r"(prmt_sel));
+    } else {
+        asm volatile("shr.b32 %0, %1, %2;" : "=r"(d) : "r"(key), "r"(shift));
+        d &= digit_mask;
+    }
+    return d;
+}
+
+template <typename ElemT, int THREADS, int IPT, int MODE, bool FULL, bool BYTE_DIGIT>
+__device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem& s, const ElemT* __restrict__ in,
+                                                   uint64_t tile_base, uint32_t valid, int shift, uint32_t digit_mask, uint32_t prmt_sel,
+                                                   uint32_t tile, uint64_t* lookback, uint64_t tag_partial, uint32_t& total,
+                                                   uint32_t& bin_start) {
     using Cfg = OnesweepConfig<ElemT, THREADS, IPT>;
-    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(smem_raw);
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t TAG_PARTIAL = (uint64_t)(tag_base + 1) << LB_TAG_SHIFT;
-    const uint64_t TAG_INCLUSIVE = (uint64_t)(tag_base + 2) << LB_TAG_SHIFT;
-
-    if (tid == 0) s.tile = atomicAdd(ticket, 1u);
-#pragma unroll
-    for (int i = tid; i < Cfg::WARPS * RADIX; i += THREADS) (&s.warp_offset[0][0])[i] = 0;
-    __syncthreads();
-    const uint32_t tile = s.tile;
-    const uint64_t tile_base = (uint64_t)tile * Cfg::TILE;
-    const uint32_t valid = (uint32_t)min((uint64_t)Cfg::TILE, n - tile_base);  // elements of this tile that exist
-    const bool full = valid == Cfg::TILE;
+    const uint32_t slice = warp * Cfg::WARP_SLICE + lane;  // tile-local index of item 0
+    const uint32_t my_offset = smem_addr(&s.warp_offset[warp][0]);
+    const uint32_t staged = smem_addr(&s.staged[0]);
 
     // ---- 1. warp-striped load + per-warp digit counts (shared-memory reductions, no return value) ----
     ElemT elem[IPT];
-    uint32_t* my_offset = s.warp_offset[warp];
-    const uint32_t slice = warp * Cfg::WARP_SLICE + lane;  // tile-local index of item 0
-    if (full) {
 #pragma unroll
-        for (int i = 0; i < IPT; ++i) elem[i] = in[tile_base + slice + i * 32];
+    for (int i = 0; i < IPT; ++i)
+        if (FULL || slice + i * 32 < valid) elem[i] = in[tile_base + slice + i * 32];
 #pragma unroll
-        for (int i = 0; i < IPT; ++i) atomicAdd(&my_offset[(Elem<ElemT>::key(elem[i]) >> shift) & digit_mask], 1u);
-    } else {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) {
-            const uint32_t local = slice + i * 32;
-            if (local < valid) {
-                elem[i] = in[tile_base + local];
-                atomicAdd(&my_offset[(Elem<ElemT>::key(elem[i]) >> shift) & digit_mask], 1u);
-            }
-        }
-    }
+    for (int i = 0; i < IPT; ++i)
+        if (FULL || slice + i * 32 < valid)
+            red_add_shared(my_offset + 4u * digit_of_opaque<BYTE_DIGIT>(Elem<ElemT>::key(elem[i]), shift, digit_mask, prmt_sel), 1u);
     __syncthreads();
 
     // ---- 2. one thread per digit: totals -> PARTIAL published early; tile-local slots for every (warp, digit) ----
-    uint32_t total = 0, bin_start = 0;
     if (tid < RADIX) {
 #pragma unroll
         for (int w = 0; w < Cfg::WARPS; ++w) total += s.warp_offset[w][tid];
-        if (tile != 0) st_relaxed_u64(&lookback[(uint64_t)tile * RADIX + tid], TAG_PARTIAL | total);
+        if (tile != 0) st_relaxed_u64(&lookback[(uint64_t)tile * RADIX + tid], tag_partial | total);
         bin_start = block_exclusive_scan_256<uint32_t>(total, s.scan_warp_total, tid);
         uint32_t run = bin_start;
 #pragma unroll
@@ -257,18 +278,58 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
     __syncthreads();
 
     // ---- 3. warp multisplit ranking; each element goes straight to its tile-local sorted slot ----
-    const uint32_t lt = lanemask_lt();
+    const uint32_t lt = lanemask_lt(), gt = lanemask_gt();
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-        const bool live = full || (slice + i * 32 < valid);
-        const uint32_t digit = live ? ((Elem<ElemT>::key(elem[i]) >> shift) & digit_mask) : (uint32_t)(RADIX - 1);
-        uint32_t peers = same_digit_lanes<MODE>(digit);
-        if (!full) peers &= __ballot_sync(0xffffffffu, live);  // padding lanes are nobody's peers
-        const uint32_t lower = peers & lt;
-        uint32_t slot = 0;
-        if (live && lower == 0) slot = atomicAdd(&my_offset[digit], (uint32_t)__popc(peers));  // lowest lane of the group
-        slot = __shfl_sync(0xffffffffu, slot, __ffs(peers | (live ? 0u : (1u << lane))) - 1);
-        if (live) s.staged[slot + __popc(lower)] = elem[i];
+        const bool live = FULL || (slice + i * 32 < valid);
+        const uint32_t digit = live ? digit_of<BYTE_DIGIT>(Elem<ElemT>::key(elem[i]), shift, digit_mask, prmt_sel) : (uint32_t)(RADIX - 1);
+        const uint32_t counter = my_offset + 4u * digit;
+        if (MODE == RANK_ATOMIC_UNORDERED) {
+            if (live) st_shared(staged + (uint32_t)sizeof(ElemT) * atom_add_shared(counter, 1u), elem[i]);
+        } else {
+            uint32_t peers = same_digit_lanes<MODE>(digit);
+            if (!FULL) {
+                const uint32_t live_lanes = __ballot_sync(0xffffffffu, live);
+                peers = live ? (peers & live_lanes) : (1u << lane);  // padding lanes are nobody's peers
+            }
+            uint32_t slot = 0;
+            if (live && (peers & gt) == 0) slot = atom_add_shared(counter, (uint32_t)__popc(peers));  // highest lane of the group
+            slot = __shfl_sync(0xffffffffu, slot, 31 - __clz(peers));
+            if (live) st_shared(staged + (uint32_t)sizeof(ElemT) * (slot + __popc(peers & lt)), elem[i]);
+        }
+    }
+}
+
+template <typename ElemT, int THREADS, int IPT, int MODE, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
+                const unsigned long long* __restrict__ ghist_pass /*[RADIX]*/, uint64_t* lookback /*[tiles][RADIX]*/,
+                uint32_t* ticket, uint32_t tag_base) {
+    using Cfg = OnesweepConfig<ElemT, THREADS, IPT>;
+    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const uint64_t TAG_PARTIAL = (uint64_t)(tag_base + 1) << LB_TAG_SHIFT;
+    const uint64_t TAG_INCLUSIVE = (uint64_t)(tag_base + 2) << LB_TAG_SHIFT;
+
+    if (tid == 0) s.tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int i = tid; i < Cfg::WARPS * RADIX; i += THREADS) (&s.warp_offset[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s.tile;
+    const uint64_t tile_base = (uint64_t)tile * Cfg::TILE;
+    const uint32_t valid = (uint32_t)min((uint64_t)Cfg::TILE, n - tile_base);  // elements of this tile that exist
+    const bool byte_digit = digit_mask == (uint32_t)(RADIX - 1);
+    const uint32_t prmt_sel = 0x4440u | (uint32_t)(shift >> 3);
+
+    uint32_t total = 0, bin_start = 0;  // meaningful in the 256 digit threads
+    if (valid == Cfg::TILE) {
+        if (byte_digit) count_rank_scatter<ElemT, THREADS, IPT, MODE, true, true>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
+        else            count_rank_scatter<ElemT, THREADS, IPT, MODE, true, false>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
+    } else {
+        count_rank_scatter<ElemT, THREADS, IPT, MODE, false, false>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
     }
 
     // ---- 4. decoupled look-back, one thread per digit ----
@@ -318,19 +379,21 @@ struct Variant {
     size_t smem;
     const char* name;
 };
-#define B200RS_VARIANT(ElemT, THREADS, IPT, MODE) \
-    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE}
+#define B200RS_VARIANT(ElemT, THREADS, IPT, MODE, MIN_CTAS) \
+    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS}
 
 template <typename ElemT> struct Variants;
 template <> struct Variants<uint32_t> {
     static const Variant* list(int* count) {
         static const Variant v[] = {
-            B200RS_VARIANT(uint32_t, 512, 16, RANK_BALLOT),
-            B200RS_VARIANT(uint32_t, 512, 16, RANK_MATCH),
-            B200RS_VARIANT(uint32_t, 256, 16, RANK_BALLOT),
-            B200RS_VARIANT(uint32_t, 512, 12, RANK_BALLOT),
-            B200RS_VARIANT(uint32_t, 512, 20, RANK_BALLOT),
-            B200RS_VARIANT(uint32_t, 1024, 8, RANK_BALLOT),
+            B200RS_VARIANT(uint32_t, 512, 20, RANK_BALLOT, 3),
+            B200RS_VARIANT(uint32_t, 512, 16, RANK_BALLOT, 3),
+            B200RS_VARIANT(uint32_t, 512, 20, RANK_BALLOT, 2),
+            B200RS_VARIANT(uint32_t, 512, 24, RANK_BALLOT, 2),
+            B200RS_VARIANT(uint32_t, 256, 24, RANK_BALLOT, 5),
+            B200RS_VARIANT(uint32_t, 1024, 12, RANK_BALLOT, 1),
+            B200RS_VARIANT(uint32_t, 512, 16, RANK_MATCH, 3),
+            B200RS_VARIANT(uint32_t, 512, 20, RANK_ATOMIC_UNORDERED, 3),
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
@@ -340,10 +403,12 @@ template <> struct Variants<uint32_t> {
 template <> struct Variants<uint2> {
     static const Variant* list(int* count) {
         static const Variant v[] = {
-            B200RS_VARIANT(uint2, 512, 16, RANK_BALLOT),
-            B200RS_VARIANT(uint2, 512, 8, RANK_BALLOT),
-            B200RS_VARIANT(uint2, 256, 16, RANK_BALLOT),
-            B200RS_VARIANT(uint2, 512, 12, RANK_BALLOT),
+            B200RS_VARIANT(uint2, 512, 16, RANK_BALLOT, 2),
+            B200RS_VARIANT(uint2, 512, 12, RANK_BALLOT, 3),
+            B200RS_VARIANT(uint2, 512, 8, RANK_BALLOT, 3),
+            B200RS_VARIANT(uint2, 256, 16, RANK_BALLOT, 5),
+            B200RS_VARIANT(uint2, 1024, 8, RANK_BALLOT, 1),
+            B200RS_VARIANT(uint2, 512, 16, RANK_ATOMIC_UNORDERED, 2),
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
