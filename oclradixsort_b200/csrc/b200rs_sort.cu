@@ -134,6 +134,7 @@ digit_histogram_unaligned_kernel(const ElemT* __restrict__ in, uint64_t n, int n
 // =================================================================================================
 // One scatter pass.
 // =================================================================================================
+constexpr int LOOKBACK_WINDOW = 4;  // predecessors fetched per look-back step (independent loads in flight)
 constexpr uint64_t LB_VALUE_MASK = (1ull << 56) - 1;
 constexpr int LB_TAG_SHIFT = 56;
 
@@ -193,11 +194,15 @@ struct OnesweepConfig {
     struct Smem {
         ElemT staged[TILE];                  // tile in tile-local sorted order
         uint32_t warp_offset[WARPS][RADIX];  // per-warp digit counts -> running tile-local slot of (warp, digit)
-        uint64_t global_delta[RADIX];        // (global start of this tile's run of digit d) - (tile-local start)
+        ElemT* run_base[RADIX];              // &out[global start of this tile's run of digit d] - (tile-local start of d)
         uint32_t scan_warp_total[RADIX / 32];
         uint32_t tile;
     };
 };
+
+// named barriers (0 is __syncthreads over the whole CTA, look-back warp included)
+#define B200RS_BAR_DIGITS 1    /* the 256 digit threads, inside block_exclusive_scan_256 */
+
 
 // 256-wide exclusive scan by threads 0..255 (8 warps); every one of those threads must call it.
 template <typename T>
@@ -261,7 +266,8 @@ __device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT
             red_add_shared(my_offset + 4u * digit_of_opaque<BYTE_DIGIT>(Elem<ElemT>::key(elem[i]), shift, digit_mask, prmt_sel), 1u);
     __syncthreads();
 
-    // ---- 2. one thread per digit: totals -> PARTIAL published early; tile-local slots for every (warp, digit) ----
+    // ---- 2. one thread per digit: totals -> PARTIAL published before the (long) ranking phase, so successors
+    //         never wait for it; tile-local slots for every (warp, digit) ----
     if (tid < RADIX) {
 #pragma unroll
         for (int w = 0; w < Cfg::WARPS; ++w) total += s.warp_offset[w][tid];
@@ -332,32 +338,38 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
         count_rank_scatter<ElemT, THREADS, IPT, MODE, false, false>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
     }
 
-    // ---- 4. decoupled look-back, one thread per digit ----
+    // ---- 4. decoupled look-back, one thread per digit, LOOKBACK_WINDOW predecessors per step ----
+    // The chain depth is (latency of one step) / (interval between tile starts): tens of tiles at full speed,
+    // so each step fetches a window of predecessors with independent loads instead of one.
     if (tid < RADIX) {
-        uint64_t exclusive;
+        uint64_t exclusive = 0;
         if (tile == 0) {
             // seed: global start of each digit = exclusive scan of the whole-input histogram
-            uint64_t* scratch = s.global_delta;  // 8 x u64 of it, not yet in use
+            uint64_t* scratch = reinterpret_cast<uint64_t*>(s.run_base);  // 8 x u64 of it, not yet in use
             exclusive = block_exclusive_scan_256<uint64_t>((uint64_t)ghist_pass[tid], scratch, tid);
         } else {
-            exclusive = 0;
-            int64_t t = (int64_t)tile - 1;
-            while (true) {
-                const uint64_t w = ld_relaxed_u64(&lookback[(uint64_t)t * RADIX + tid]);
-                const uint64_t tag = w & ~LB_VALUE_MASK;
-                if (tag == TAG_INCLUSIVE) {
-                    exclusive += w & LB_VALUE_MASK;
-                    break;
+            int64_t t = (int64_t)tile - 1;  // tile 0 always publishes INCLUSIVE, so the walk ends at t >= 0
+            bool done = false;
+            while (!done) {
+                uint64_t w[LOOKBACK_WINDOW];
+#pragma unroll
+                for (int j = 0; j < LOOKBACK_WINDOW; ++j)
+                    w[j] = (t - j >= 0) ? ld_relaxed_u64(&lookback[(uint64_t)(t - j) * RADIX + tid]) : 0ull;
+                int consumed = 0;
+#pragma unroll
+                for (int j = 0; j < LOOKBACK_WINDOW; ++j) {
+                    const uint64_t tag = w[j] & ~LB_VALUE_MASK;
+                    if (!done && consumed == j && (tag == TAG_INCLUSIVE || tag == TAG_PARTIAL)) {
+                        exclusive += w[j] & LB_VALUE_MASK;
+                        consumed = j + 1;
+                        done = tag == TAG_INCLUSIVE;
+                    }
                 }
-                if (tag == TAG_PARTIAL) {
-                    exclusive += w & LB_VALUE_MASK;
-                    --t;  // tile 0 always publishes INCLUSIVE, so t never goes negative
-                }
-                // anything else: not published yet for this pass -> poll again
+                t -= consumed;  // entries not yet published for this pass are polled again
             }
         }
         st_relaxed_u64(&lookback[(uint64_t)tile * RADIX + tid], TAG_INCLUSIVE | (exclusive + total));
-        s.global_delta[tid] = exclusive - bin_start;
+        s.run_base[tid] = out + exclusive - bin_start;
     }
     __syncthreads();
 
@@ -366,7 +378,7 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
     for (uint32_t j = tid; j < valid; j += THREADS) {
         const ElemT e = s.staged[j];
         const uint32_t d = (Elem<ElemT>::key(e) >> shift) & digit_mask;
-        out[s.global_delta[d] + j] = e;
+        s.run_base[d][j] = e;
     }
 }
 
@@ -388,10 +400,10 @@ template <> struct Variants<uint32_t> {
         static const Variant v[] = {
             B200RS_VARIANT(uint32_t, 512, 20, RANK_BALLOT, 3),
             B200RS_VARIANT(uint32_t, 512, 16, RANK_BALLOT, 3),
-            B200RS_VARIANT(uint32_t, 512, 20, RANK_BALLOT, 2),
-            B200RS_VARIANT(uint32_t, 512, 24, RANK_BALLOT, 2),
-            B200RS_VARIANT(uint32_t, 256, 24, RANK_BALLOT, 5),
-            B200RS_VARIANT(uint32_t, 1024, 12, RANK_BALLOT, 1),
+            B200RS_VARIANT(uint32_t, 512, 24, RANK_BALLOT, 3),
+            B200RS_VARIANT(uint32_t, 384, 24, RANK_BALLOT, 4),
+            B200RS_VARIANT(uint32_t, 256, 24, RANK_BALLOT, 6),
+            B200RS_VARIANT(uint32_t, 1024, 16, RANK_BALLOT, 1),
             B200RS_VARIANT(uint32_t, 512, 16, RANK_MATCH, 3),
             B200RS_VARIANT(uint32_t, 512, 20, RANK_ATOMIC_UNORDERED, 3),
         };
@@ -405,9 +417,9 @@ template <> struct Variants<uint2> {
         static const Variant v[] = {
             B200RS_VARIANT(uint2, 512, 16, RANK_BALLOT, 2),
             B200RS_VARIANT(uint2, 512, 12, RANK_BALLOT, 3),
-            B200RS_VARIANT(uint2, 512, 8, RANK_BALLOT, 3),
+            B200RS_VARIANT(uint2, 384, 16, RANK_BALLOT, 3),
             B200RS_VARIANT(uint2, 256, 16, RANK_BALLOT, 5),
-            B200RS_VARIANT(uint2, 1024, 8, RANK_BALLOT, 1),
+            B200RS_VARIANT(uint2, 1024, 12, RANK_BALLOT, 1),
             B200RS_VARIANT(uint2, 512, 16, RANK_ATOMIC_UNORDERED, 2),
         };
         *count = sizeof(v) / sizeof(v[0]);
