@@ -181,6 +181,12 @@ __device__ __forceinline__ uint32_t atom_add_shared(uint32_t addr, uint32_t v) {
     asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
     return old;
 }
+// atomicAdd executed only where `pred` is set (predicated instruction, no divergent branch); returns 0 elsewhere
+__device__ __forceinline__ uint32_t atom_add_shared_if(bool pred, uint32_t addr, uint32_t v) {
+    uint32_t old = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p atom.shared.add.u32 %0, [%1], %2;\n\t}" : "+r"(old) : "r"(addr), "r"(v), "r"((uint32_t)pred) : "memory");
+    return old;
+}
 __device__ __forceinline__ void st_shared(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_shared(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
@@ -194,7 +200,7 @@ struct OnesweepConfig {
     struct Smem {
         ElemT staged[TILE];                  // tile in tile-local sorted order
         uint32_t warp_offset[WARPS][RADIX];  // per-warp digit counts -> running tile-local slot of (warp, digit)
-        ElemT* run_base[RADIX];              // &out[global start of this tile's run of digit d] - (tile-local start of d)
+        uint64_t run_start[RADIX];           // (global start of this tile's run of digit d) - (tile-local start of d)
         uint32_t scan_warp_total[RADIX / 32];
         uint32_t tile;
     };
@@ -257,9 +263,10 @@ __device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT
 
     // ---- 1. warp-striped load + per-warp digit counts (shared-memory reductions, no return value) ----
     ElemT elem[IPT];
+    const ElemT* __restrict__ src = in + tile_base + slice;  // one base register, immediate offsets
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
-        if (FULL || slice + i * 32 < valid) elem[i] = in[tile_base + slice + i * 32];
+        if (FULL || slice + i * 32 < valid) elem[i] = src[i * 32];
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
         if (FULL || slice + i * 32 < valid)
@@ -298,8 +305,8 @@ __device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT
                 const uint32_t live_lanes = __ballot_sync(0xffffffffu, live);
                 peers = live ? (peers & live_lanes) : (1u << lane);  // padding lanes are nobody's peers
             }
-            uint32_t slot = 0;
-            if (live && (peers & gt) == 0) slot = atom_add_shared(counter, (uint32_t)__popc(peers));  // highest lane of the group
+            // the highest lane of each group claims slots for the whole group
+            uint32_t slot = atom_add_shared_if(live && (peers & gt) == 0, counter, (uint32_t)__popc(peers));
             slot = __shfl_sync(0xffffffffu, slot, 31 - __clz(peers));
             if (live) st_shared(staged + (uint32_t)sizeof(ElemT) * (slot + __popc(peers & lt)), elem[i]);
         }
@@ -341,44 +348,58 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
     // ---- 4. decoupled look-back, one thread per digit, LOOKBACK_WINDOW predecessors per step ----
     // The chain depth is (latency of one step) / (interval between tile starts): tens of tiles at full speed,
     // so each step fetches a window of predecessors with independent loads instead of one.
+    const bool wide = (n >> 32) != 0;  // element indices need 64 bits
     if (tid < RADIX) {
         uint64_t exclusive = 0;
         if (tile == 0) {
             // seed: global start of each digit = exclusive scan of the whole-input histogram
-            uint64_t* scratch = reinterpret_cast<uint64_t*>(s.run_base);  // 8 x u64 of it, not yet in use
+            uint64_t* scratch = s.run_start;  // 8 x u64 of it, not yet in use
             exclusive = block_exclusive_scan_256<uint64_t>((uint64_t)ghist_pass[tid], scratch, tid);
         } else {
-            int64_t t = (int64_t)tile - 1;  // tile 0 always publishes INCLUSIVE, so the walk ends at t >= 0
+            const uint32_t tag_partial_hi = (tag_base + 1) << (LB_TAG_SHIFT - 32), tag_inclusive_hi = (tag_base + 2) << (LB_TAG_SHIFT - 32);
+            const uint64_t* p = lookback + (uint64_t)(tile - 1) * RADIX + tid;  // tile 0 always publishes INCLUSIVE: the walk ends there
+            int32_t ahead = (int32_t)tile;                                     // predecessors that exist below and including *p
             bool done = false;
             while (!done) {
                 uint64_t w[LOOKBACK_WINDOW];
 #pragma unroll
-                for (int j = 0; j < LOOKBACK_WINDOW; ++j)
-                    w[j] = (t - j >= 0) ? ld_relaxed_u64(&lookback[(uint64_t)(t - j) * RADIX + tid]) : 0ull;
+                for (int j = 0; j < LOOKBACK_WINDOW; ++j) w[j] = j < ahead ? ld_relaxed_u64(p - j * RADIX) : 0ull;
                 int consumed = 0;
 #pragma unroll
                 for (int j = 0; j < LOOKBACK_WINDOW; ++j) {
-                    const uint64_t tag = w[j] & ~LB_VALUE_MASK;
-                    if (!done && consumed == j && (tag == TAG_INCLUSIVE || tag == TAG_PARTIAL)) {
+                    const uint32_t tag_hi = (uint32_t)(w[j] >> 32) & 0xff000000u;
+                    const bool inclusive = tag_hi == tag_inclusive_hi;
+                    if (!done && consumed == j && (inclusive || tag_hi == tag_partial_hi)) {
                         exclusive += w[j] & LB_VALUE_MASK;
                         consumed = j + 1;
-                        done = tag == TAG_INCLUSIVE;
+                        done = inclusive;
                     }
                 }
-                t -= consumed;  // entries not yet published for this pass are polled again
+                p -= consumed * RADIX;  // entries not yet published for this pass are polled again
+                ahead -= consumed;
             }
         }
         st_relaxed_u64(&lookback[(uint64_t)tile * RADIX + tid], TAG_INCLUSIVE | (exclusive + total));
-        s.run_base[tid] = out + exclusive - bin_start;
+        s.run_start[tid] = exclusive - bin_start;  // out index of the element at tile-local slot j of digit d: run_start[d] + j
     }
     __syncthreads();
 
     // ---- 5. write the tile out in sorted order ----
+    if (!wide) {
+        const uint32_t* run_start32 = reinterpret_cast<const uint32_t*>(s.run_start);  // low words (little endian)
 #pragma unroll 4
-    for (uint32_t j = tid; j < valid; j += THREADS) {
-        const ElemT e = s.staged[j];
-        const uint32_t d = (Elem<ElemT>::key(e) >> shift) & digit_mask;
-        s.run_base[d][j] = e;
+        for (uint32_t j = tid; j < valid; j += THREADS) {
+            const ElemT e = s.staged[j];
+            const uint32_t d = byte_digit ? __byte_perm(Elem<ElemT>::key(e), 0u, prmt_sel) : ((Elem<ElemT>::key(e) >> shift) & digit_mask);
+            out[run_start32[2 * d] + j] = e;  // 32-bit index arithmetic (wraps correctly: the true index is < 2^32)
+        }
+    } else {
+#pragma unroll 4
+        for (uint32_t j = tid; j < valid; j += THREADS) {
+            const ElemT e = s.staged[j];
+            const uint32_t d = (Elem<ElemT>::key(e) >> shift) & digit_mask;
+            out[s.run_start[d] + j] = e;
+        }
     }
 }
 
@@ -398,14 +419,13 @@ template <typename ElemT> struct Variants;
 template <> struct Variants<uint32_t> {
     static const Variant* list(int* count) {
         static const Variant v[] = {
+            B200RS_VARIANT(uint32_t, 512, 24, RANK_BALLOT, 3),  // default
             B200RS_VARIANT(uint32_t, 512, 20, RANK_BALLOT, 3),
             B200RS_VARIANT(uint32_t, 512, 16, RANK_BALLOT, 3),
-            B200RS_VARIANT(uint32_t, 512, 24, RANK_BALLOT, 3),
             B200RS_VARIANT(uint32_t, 384, 24, RANK_BALLOT, 4),
-            B200RS_VARIANT(uint32_t, 256, 24, RANK_BALLOT, 6),
             B200RS_VARIANT(uint32_t, 1024, 16, RANK_BALLOT, 1),
-            B200RS_VARIANT(uint32_t, 512, 16, RANK_MATCH, 3),
-            B200RS_VARIANT(uint32_t, 512, 20, RANK_ATOMIC_UNORDERED, 3),
+            B200RS_VARIANT(uint32_t, 512, 16, RANK_MATCH, 3),             // measurement only
+            B200RS_VARIANT(uint32_t, 512, 20, RANK_ATOMIC_UNORDERED, 3),  // measurement only, not stable by contract
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
@@ -415,19 +435,18 @@ template <> struct Variants<uint32_t> {
 template <> struct Variants<uint2> {
     static const Variant* list(int* count) {
         static const Variant v[] = {
+            B200RS_VARIANT(uint2, 384, 16, RANK_BALLOT, 3),  // default
             B200RS_VARIANT(uint2, 512, 16, RANK_BALLOT, 2),
             B200RS_VARIANT(uint2, 512, 12, RANK_BALLOT, 3),
-            B200RS_VARIANT(uint2, 384, 16, RANK_BALLOT, 3),
-            B200RS_VARIANT(uint2, 256, 16, RANK_BALLOT, 5),
             B200RS_VARIANT(uint2, 1024, 12, RANK_BALLOT, 1),
-            B200RS_VARIANT(uint2, 512, 16, RANK_ATOMIC_UNORDERED, 2),
+            B200RS_VARIANT(uint2, 512, 16, RANK_ATOMIC_UNORDERED, 2),  // measurement only, not stable by contract
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
     }
     static const char* env() { return "B200RS_PAIRS_VARIANT"; }
 };
-constexpr uint64_t MIN_TILE = 256 * 16;  // smallest tile among the variants: temp storage is sized for it
+constexpr uint64_t MIN_TILE = 384 * 16;  // smallest tile among the variants: temp storage is sized for it
 
 template <typename ElemT>
 const Variant& pick_variant() {
