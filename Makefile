@@ -13,7 +13,13 @@ SRCS   := $(CSRC)/b200rs_device.cu $(CSRC)/b200rs_scan.cu $(CSRC)/b200rs_sort.cu
 OBJS   := $(SRCS:.cu=.o)
 LIB    := oclradixsort_b200/libb200rs.so
 
-all: $(LIB)
+TAHOE_LIB := oclradixsort_b200/libtahoe_pprims.so
+
+all: $(LIB) $(TAHOE_LIB)
+
+# Tahoe::Pprims (C++ drop-in, include/Tahoe/ParallelPrimitives/Pprims.h) for C++ callers; plain g++, links libb200rs.so
+$(TAHOE_LIB): $(CSRC)/Pprims.cpp $(LIB) $(wildcard include/Adl/*.h include/Tahoe/*/*.h include/Tahoe/*/*/*.h)
+	$(CXX) -std=c++11 -O2 -Wall -fPIC -shared -Iinclude $(CSRC)/Pprims.cpp -Loclradixsort_b200 -lb200rs -Wl,-rpath,'$$ORIGIN' -o $@
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/b200rs_internal.h include/b200rs.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(@:.o=.ptxas.log) || (cat $(@:.o=.ptxas.log); false)
@@ -26,6 +32,23 @@ oracle:
 	if [ -d $(REF) ]; then $(MAKE) -C oracle ref; fi
 
 clean:
-	rm -f $(OBJS) $(CSRC)/*.ptxas.log $(LIB)
+	rm -f $(OBJS) $(CSRC)/*.ptxas.log $(LIB) $(TAHOE_LIB)
 
 .PHONY: all oracle clean
+
+# ---- drop-in check: the reference's UNCHANGED UnitTest/main.cpp against include/ + libb200rs.so ----
+# Built only where $(REF) exists (the build container); the binary travels to the GPU box in oracle/_ref/.
+# The CPU side of the comparison (Tahoe::RadixSort::sort) is the reference's own RadixSort.cpp.
+UT_DEFS := -DNDEBUG -DTH_LOG_LEVEL=3 -DTH_UNIT_TEST -DTH_NON_WINDOW_TEST -D__LINUX__ -D_X64   # premake4.lua:23,42,46,61,81
+UT_OUT  := oracle/_ref
+
+unittest: $(LIB)
+	mkdir -p $(UT_OUT)
+	test -f $(UT_OUT)/gtest-all.o || $(CXX) -std=c++11 -O1 -w -I$(REF)/contrib/include -I$(REF)/contrib/src/gtest-1.6.0 -c $(REF)/contrib/src/gtest-1.6.0/gtest-all.cc -o $(UT_OUT)/gtest-all.o
+	$(CXX) -std=c++11 -O2 -w $(UT_DEFS) -Iinclude -I$(REF)/contrib/include \
+	    $(REF)/UnitTest/main.cpp $(CSRC)/Pprims.cpp $(REF)/Tahoe/Algorithm/Sort/RadixSort.cpp $(UT_OUT)/gtest-all.o \
+	    -Loclradixsort_b200 -lb200rs -lpthread -Wl,-rpath,'$$ORIGIN/../../oclradixsort_b200' -o $(UT_OUT)/UnitTest64
+
+# Same program, but with the CPU check provided by the repo's own oracle (buildable without $(REF) sources
+# except main.cpp/gtest, kept for symmetry; not used on the GPU box).
+.PHONY: unittest

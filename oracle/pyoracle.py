@@ -69,6 +69,9 @@ def ref() -> ctypes.CDLL:
                      "ref_hostbackend_sort_pairs"):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_int]
             getattr(L, name).restype = None
+        for name in ("ref_hostbackend_sort_u32_timed", "ref_hostbackend_sort_pairs_timed"):
+            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_int]
+            getattr(L, name).restype = ctypes.c_double
         _ref = L
     return _ref
 
@@ -140,3 +143,10 @@ def ref_sort_pairs(pairs: np.ndarray, host_backend: bool = False) -> np.ndarray:
     fn = ref().ref_hostbackend_sort_pairs if host_backend else ref().ref_radixsort_pairs
     fn(_ptr(out), out.shape[0])
     return out
+
+
+def ref_time_hostbackend(data: np.ndarray, pairs: bool) -> float:
+    """Seconds the UNMODIFIED reference's Host-backend Pprims::radixSort takes on `data` (sorted in place)."""
+    assert data.flags["C_CONTIGUOUS"]
+    fn = ref().ref_hostbackend_sort_pairs_timed if pairs else ref().ref_hostbackend_sort_u32_timed
+    return float(fn(_ptr(data), data.shape[0]))
