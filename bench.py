@@ -218,11 +218,13 @@ def main() -> None:
         bufs = [fresh_pairs() for _ in range(nbuf)]
         handles = [ob.Buffer(dev, n, ob.PAIR_DTYPE, ptr=b.data_ptr()) for b in bufs]
 
+        last = {}
+
         def step(i):
             if sorter is None:
                 pp.radixSort(dev, handles[i], n, 32)
             else:
-                sorter.sort(handles[i], n)
+                last["out"], last["m"] = sorter.sort(handles[i], n)
 
         for i in range(args.warmup):
             step(i)
@@ -255,14 +257,28 @@ def main() -> None:
         ms_per_step = ms / args.steps
         value = world * n / (ms_per_step * 1e-3) / 1e9
 
-        # sanity: the last timed buffer is sorted, stable, and a permutation of what was generated
-        k64 = bufs[-1][:, 0].to(torch.int64) & 0xFFFFFFFF
-        ok_sorted = bool((k64[1:] >= k64[:-1]).all())
+        # sanity: the last timed step's output is sorted, stable, and a permutation of what was generated
         if sorter is None:
+            k64 = bufs[-1][:, 0].to(torch.int64) & 0xFFFFFFFF
             same = k64[1:] == k64[:-1]
             v = bufs[-1][:, 1]
-            ok_sorted = ok_sorted and bool((v[1:][same] > v[:-1][same]).all()) and int(v.to(torch.int64).sum().item()) == n * (n - 1) // 2
-        del k64
+            ok_sorted = bool((k64[1:] >= k64[:-1]).all()) and bool((v[1:][same] > v[:-1][same]).all()) \
+                and int(v.to(torch.int64).sum().item()) == n * (n - 1) // 2
+            del k64, same
+        else:
+            out, m = last["out"], last["m"]
+            k64 = out & 0xFFFFFFFF  # key = low half of the 8-byte pair
+            ok_local = bool((k64[1:] >= k64[:-1]).all()) if m > 1 else True
+            lo = int(k64[0].item()) if m else 2**32
+            hi = int(k64[-1].item()) if m else -1
+            stats = torch.tensor([m, lo, hi, int(ok_local)], device="cuda", dtype=torch.int64)
+            allstats = [torch.empty_like(stats) for _ in range(world)]
+            dist.all_gather(allstats, stats)
+            rows = [t.tolist() for t in allstats]
+            nonempty = [r for r in rows if r[0] > 0]
+            ok_sorted = all(r[3] == 1 for r in rows) and sum(r[0] for r in rows) == world * n \
+                and all(a[2] <= b[1] for a, b in zip(nonempty, nonempty[1:]))  # rank r's largest key <= rank r+1's smallest
+            del k64
         if not ok_sorted:
             raise SystemExit("bench.py: output of the last timed step is not a stable sort of its input")
 

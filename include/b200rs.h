@@ -109,6 +109,16 @@ int b200rs_exclusive_scan_u32(b200rs_device* dev, uint32_t* dst, const uint32_t*
                               void* temp, size_t* temp_bytes);
 
 /*
+ * Building blocks of the multi-GPU partitioned sort (new capability; the reference is single-device, SURVEY.md
+ * section 8e).  Histogram of one key digit, and a STABLE partition of pairs by a 256-entry digit -> part table:
+ * `out` receives part 0, then part 1, ... each in input order; part_counts[p] (device, 256 x u64, zero for unused
+ * parts) must hold the number of elements of part p, e.g. summed from b200rs_digit_histogram_pairs.
+ */
+int b200rs_digit_histogram_pairs(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, int bits, uint64_t* hist_out);
+int b200rs_partition_pairs(b200rs_device* dev, const b200rs_pair* in, b200rs_pair* out, uint64_t n, int shift, int bits,
+                           const uint8_t* digit_to_part, const uint64_t* part_counts, void* temp, size_t* temp_bytes);
+
+/*
  * HOST-buffer forms: what a caller holding CPU arrays uses in place of the reference's
  * "getHostPtr / fill / returnHostPtr / radixSort / getHostPtr / read" sequence
  * (UnitTest/main.cpp:118-139).  Host -> device copy, sort/scan, device -> host copy, stream sync;

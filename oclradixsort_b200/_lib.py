@@ -47,6 +47,8 @@ SIGNATURES = {
     "b200rs_sort_keys_u32": (_int, [c_dev, _vp, _u64, _int, _vp, _P(_sz)]),
     "b200rs_sort_pairs_u32": (_int, [c_dev, _vp, _u64, _int, _vp, _P(_sz)]),
     "b200rs_exclusive_scan_u32": (_int, [c_dev, _vp, _vp, _u64, _vp, _vp, _P(_sz)]),
+    "b200rs_digit_histogram_pairs": (_int, [c_dev, _vp, _u64, _int, _int, _vp]),
+    "b200rs_partition_pairs": (_int, [c_dev, _vp, _vp, _u64, _int, _int, _vp, _vp, _vp, _P(_sz)]),
     "b200rs_sort_keys_u32_host": (_int, [c_dev, _vp, _u64, _int]),
     "b200rs_sort_pairs_u32_host": (_int, [c_dev, _vp, _u64, _int]),
     "b200rs_exclusive_scan_u32_host": (_int, [c_dev, _vp, _vp, _u64, _P(ctypes.c_uint32)]),

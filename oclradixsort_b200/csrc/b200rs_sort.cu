@@ -203,6 +203,7 @@ struct OnesweepConfig {
         uint64_t run_start[RADIX];           // (global start of this tile's run of digit d) - (tile-local start of d)
         uint32_t scan_warp_total[RADIX / 32];
         uint32_t tile;
+        uint8_t lut[RADIX];                  // partition passes only: raw digit -> part (see onesweep_kernel<..., LUT>)
     };
 };
 
@@ -250,7 +251,7 @@ __device__ __forceinline__ uint32_t digit_of_opaque(uint32_t key, int shift, uin
     return d;
 }
 
-template <typename ElemT, int THREADS, int IPT, int MODE, bool FULL, bool BYTE_DIGIT>
+template <typename ElemT, int THREADS, int IPT, int MODE, bool FULL, bool BYTE_DIGIT, bool LUT>
 __device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem& s, const ElemT* __restrict__ in,
                                                    uint64_t tile_base, uint32_t valid, int shift, uint32_t digit_mask, uint32_t prmt_sel,
                                                    uint32_t tile, uint64_t* lookback, uint64_t tag_partial, uint32_t& total,
@@ -270,7 +271,11 @@ __device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
         if (FULL || slice + i * 32 < valid)
-            red_add_shared(my_offset + 4u * digit_of_opaque<BYTE_DIGIT>(Elem<ElemT>::key(elem[i]), shift, digit_mask, prmt_sel), 1u);
+        {
+            uint32_t d = digit_of_opaque<BYTE_DIGIT>(Elem<ElemT>::key(elem[i]), shift, digit_mask, prmt_sel);
+            if (LUT) d = s.lut[d];
+            red_add_shared(my_offset + 4u * d, 1u);
+        }
     __syncthreads();
 
     // ---- 2. one thread per digit: totals -> PARTIAL published before the (long) ranking phase, so successors
@@ -295,7 +300,8 @@ __device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         const bool live = FULL || (slice + i * 32 < valid);
-        const uint32_t digit = live ? digit_of<BYTE_DIGIT>(Elem<ElemT>::key(elem[i]), shift, digit_mask, prmt_sel) : (uint32_t)(RADIX - 1);
+        uint32_t digit = live ? digit_of<BYTE_DIGIT>(Elem<ElemT>::key(elem[i]), shift, digit_mask, prmt_sel) : (uint32_t)(RADIX - 1);
+        if (LUT && live) digit = s.lut[digit];
         const uint32_t counter = my_offset + 4u * digit;
         if (MODE == RANK_ATOMIC_UNORDERED) {
             if (live) st_shared(staged + (uint32_t)sizeof(ElemT) * atom_add_shared(counter, 1u), elem[i]);
@@ -313,11 +319,14 @@ __device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT
     }
 }
 
-template <typename ElemT, int THREADS, int IPT, int MODE, int MIN_CTAS>
+// LUT = true turns the pass into a stable PARTITION: the raw digit is mapped through digit_lut (256 bytes) to a part
+// id, ghist_pass holds the element count of every part, and the output is the parts laid out one after another in
+// part order.  Used by the multi-GPU sort to group elements by destination GPU (oclradixsort_b200/dist.py).
+template <typename ElemT, int THREADS, int IPT, int MODE, int MIN_CTAS, bool LUT = false>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
                 const unsigned long long* __restrict__ ghist_pass /*[RADIX]*/, uint64_t* lookback /*[tiles][RADIX]*/,
-                uint32_t* ticket, uint32_t tag_base) {
+                uint32_t* ticket, uint32_t tag_base, const uint8_t* __restrict__ digit_lut) {
     using Cfg = OnesweepConfig<ElemT, THREADS, IPT>;
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -330,19 +339,20 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
     if (tid == 0) s.tile = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int i = tid; i < Cfg::WARPS * RADIX; i += THREADS) (&s.warp_offset[0][0])[i] = 0;
+    if (LUT && tid < RADIX) s.lut[tid] = digit_lut[tid];
     __syncthreads();
     const uint32_t tile = s.tile;
     const uint64_t tile_base = (uint64_t)tile * Cfg::TILE;
     const uint32_t valid = (uint32_t)min((uint64_t)Cfg::TILE, n - tile_base);  // elements of this tile that exist
-    const bool byte_digit = digit_mask == (uint32_t)(RADIX - 1);
+    const bool byte_digit = !LUT && digit_mask == (uint32_t)(RADIX - 1);
     const uint32_t prmt_sel = 0x4440u | (uint32_t)(shift >> 3);
 
     uint32_t total = 0, bin_start = 0;  // meaningful in the 256 digit threads
     if (valid == Cfg::TILE) {
-        if (byte_digit) count_rank_scatter<ElemT, THREADS, IPT, MODE, true, true>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
-        else            count_rank_scatter<ElemT, THREADS, IPT, MODE, true, false>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
+        if (byte_digit) count_rank_scatter<ElemT, THREADS, IPT, MODE, true, !LUT, LUT>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
+        else            count_rank_scatter<ElemT, THREADS, IPT, MODE, true, false, LUT>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
     } else {
-        count_rank_scatter<ElemT, THREADS, IPT, MODE, false, false>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
+        count_rank_scatter<ElemT, THREADS, IPT, MODE, false, false, LUT>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
     }
 
     // ---- 4. decoupled look-back, one thread per digit, LOOKBACK_WINDOW predecessors per step ----
@@ -390,14 +400,16 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
 #pragma unroll 4
         for (uint32_t j = tid; j < valid; j += THREADS) {
             const ElemT e = s.staged[j];
-            const uint32_t d = byte_digit ? __byte_perm(Elem<ElemT>::key(e), 0u, prmt_sel) : ((Elem<ElemT>::key(e) >> shift) & digit_mask);
+            uint32_t d = byte_digit ? __byte_perm(Elem<ElemT>::key(e), 0u, prmt_sel) : ((Elem<ElemT>::key(e) >> shift) & digit_mask);
+            if (LUT) d = s.lut[d];
             out[run_start32[2 * d] + j] = e;  // 32-bit index arithmetic (wraps correctly: the true index is < 2^32)
         }
     } else {
 #pragma unroll 4
         for (uint32_t j = tid; j < valid; j += THREADS) {
             const ElemT e = s.staged[j];
-            const uint32_t d = (Elem<ElemT>::key(e) >> shift) & digit_mask;
+            uint32_t d = (Elem<ElemT>::key(e) >> shift) & digit_mask;
+            if (LUT) d = s.lut[d];
             out[s.run_start[d] + j] = e;
         }
     }
@@ -535,7 +547,8 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         uint32_t* ticket = tickets + p;
         uint32_t tag_base = (uint32_t)(2 * p);
         uint64_t n_arg = n;
-        void* args[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lookback, &ticket, &tag_base};
+        const uint8_t* no_lut = nullptr;
+        void* args[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lookback, &ticket, &tag_base, &no_lut};
         snprintf(label, sizeof(label), "onesweep_%s_pass%d", what, p);
         {
             b200rs_launch_scope scope(dev, label, n, 2ull * n * sizeof(ElemT));
@@ -548,7 +561,80 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     return B200RS_OK;
 }
 
+// ---- pieces of the multi-GPU sort (pairs) -----------------------------------------------------------
+
+// Histogram of ONE digit (key >> shift) & mask, overwriting out[0..255].
+template <typename ElemT>
+__global__ void __launch_bounds__(HIST_THREADS)
+single_digit_histogram_kernel(const ElemT* __restrict__ in, uint64_t n, int shift, uint32_t mask, unsigned long long* __restrict__ out) {
+    __shared__ uint32_t s_hist[RADIX];
+    for (int i = threadIdx.x; i < RADIX; i += HIST_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * HIST_THREADS;
+    uint64_t i = (uint64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        uint32_t k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) k[u] = Elem<ElemT>::key(in[i + u * stride]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) atomicAdd(&s_hist[(k[u] >> shift) & mask], 1u);
+    }
+    for (; i < n; i += stride) atomicAdd(&s_hist[(Elem<ElemT>::key(in[i]) >> shift) & mask], 1u);
+    __syncthreads();
+    for (int b = threadIdx.x; b < RADIX; b += HIST_THREADS)
+        if (s_hist[b]) atomicAdd(&out[b], (unsigned long long)s_hist[b]);
+}
+
+constexpr int PART_THREADS = 384, PART_IPT = 16;  // same shape as the default pair scatter pass
+
 }  // namespace
+
+extern "C" int b200rs_digit_histogram_pairs(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, int bits, uint64_t* hist_out) {
+    if (!dev || !hist_out || (n && !in) || shift < 0 || bits < 1 || bits > RADIX_BITS || shift + bits > 32) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    B200RS_CUDA(cudaMemsetAsync(hist_out, 0, sizeof(uint64_t) * RADIX, dev->stream));
+    if (n == 0) return B200RS_OK;
+    uint64_t blocks = (n + (uint64_t)HIST_THREADS * 8 - 1) / ((uint64_t)HIST_THREADS * 8);
+    if (blocks > (uint64_t)dev->num_sms * 4) blocks = (uint64_t)dev->num_sms * 4;
+    {
+        b200rs_launch_scope scope(dev, "single_digit_histogram_pairs", n, n * sizeof(uint2));
+        single_digit_histogram_kernel<uint2><<<(unsigned)blocks, HIST_THREADS, 0, dev->stream>>>(
+            reinterpret_cast<const uint2*>(in), n, shift, (1u << bits) - 1u, reinterpret_cast<unsigned long long*>(hist_out));
+    }
+    B200RS_CUDA(cudaGetLastError());
+    return B200RS_OK;
+}
+
+extern "C" int b200rs_partition_pairs(b200rs_device* dev, const b200rs_pair* in, b200rs_pair* out, uint64_t n, int shift, int bits,
+                                      const uint8_t* digit_to_part, const uint64_t* part_counts, void* temp, size_t* temp_bytes) {
+    using Cfg = OnesweepConfig<uint2, PART_THREADS, PART_IPT>;
+    if (!dev || !temp_bytes || shift < 0 || bits < 1 || bits > RADIX_BITS || shift + bits > 32) return B200RS_ERR_INVALID_ARGUMENT;
+    const uint64_t tiles = (n + Cfg::TILE - 1) / Cfg::TILE;
+    if (tiles > 0x7fffffffull) return B200RS_ERR_TOO_LARGE;
+    const size_t need = 256 + b200rs_align_up((size_t)tiles * RADIX * sizeof(uint64_t), 256);
+    if (!temp) {
+        *temp_bytes = need;
+        return B200RS_OK;
+    }
+    if (*temp_bytes < need) return B200RS_ERR_TEMP_TOO_SMALL;
+    if (n == 0) return B200RS_OK;
+    if (!in || !out || !digit_to_part || !part_counts || ((uintptr_t)temp & 255u) || (((uintptr_t)in | (uintptr_t)out) & 7u)) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    B200RS_CUDA(cudaMemsetAsync(temp, 0, need, dev->stream));
+    auto kernel = onesweep_kernel<uint2, PART_THREADS, PART_IPT, RANK_BALLOT, 3, true>;
+    const size_t smem = sizeof(typename Cfg::Smem);
+    B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(temp);
+    uint64_t* lookback = reinterpret_cast<uint64_t*>(static_cast<char*>(temp) + 256);
+    {
+        b200rs_launch_scope scope(dev, "partition_pairs", n, 2ull * n * sizeof(uint2));
+        kernel<<<(unsigned)tiles, PART_THREADS, smem, dev->stream>>>(reinterpret_cast<const uint2*>(in), reinterpret_cast<uint2*>(out), n, shift,
+                                                                     (1u << bits) - 1u, reinterpret_cast<const unsigned long long*>(part_counts),
+                                                                     lookback, ticket, 0u, digit_to_part);
+    }
+    B200RS_CUDA(cudaGetLastError());
+    return B200RS_OK;
+}
 
 extern "C" int b200rs_sort_keys_u32(b200rs_device* dev, uint32_t* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes) {
     return sort_impl<uint32_t>(dev, inout, n, sort_bits, temp, temp_bytes, "keys");

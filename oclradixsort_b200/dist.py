@@ -1,0 +1,191 @@
+"""Partitioned key-value sort across the GPUs of one box (new capability -- the reference is
+single-device, one cl_context + one in-order queue, Adl/CL/AdlCL.inl:284-303).
+
+One process per GPU, torch.distributed for the plumbing.  Rank r holds a slice of the input; slices in rank order
+are the global input order.  For inputs beyond one GPU's HBM:
+
+  1. local histogram of the TOP key digit (8 bits)                        b200rs_digit_histogram_pairs
+  2. all-gather of the per-rank histograms (256 x P counts)               dist.all_gather_into_tensor  (NCCL)
+     -> every rank derives the same plan: contiguous digit ranges -> ranks with about N/P pairs each
+  3. local STABLE partition by destination rank                           b200rs_partition_pairs
+  4. exchange, receive slots ordered by source rank                       dist.all_to_all_single over NVLink (NCCL)
+  5. local stable LSD sort of what was received                           b200rs_sort_pairs_u32
+
+Bit-exactness: 3 and 5 are stable and 4 keeps (source rank, position) order = global input order inside every
+destination, and destinations own disjoint, increasing key ranges, so the concatenation of the ranks' outputs is
+exactly the single stable sort of the concatenated input.  Outputs differ in length under skew; a destination
+whose share exceeds its receive capacity raises (no silent truncation, no CPU fallback).
+
+The device work is injected through a small `ops` object so the protocol (plan, split sizes, ordering) can be
+exercised on CPU with gloo in tests/ -- the product uses CudaLocalOps only.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from ._lib import B200RSError, check, lib
+
+TOP_SHIFT, TOP_BITS, NUM_BINS = 24, 8, 256
+ERR_CAPACITY = -7  # B200RS_ERR_CAPACITY
+
+
+def plan_exchange(hist: np.ndarray) -> dict:
+    """hist[s, b] = number of pairs on source rank s whose top digit is b  (shape P x 256, any integer dtype).
+
+    Returns the plan every rank computes identically:
+      bin_to_rank[256]   owner of each digit: contiguous, non-decreasing ranges with totals close to N/P
+      send_counts[s, d]  pairs rank s sends to rank d
+      recv_total[d]      pairs rank d ends up with
+    """
+    hist = np.asarray(hist, dtype=np.int64)
+    P = hist.shape[0]
+    assert hist.shape == (P, NUM_BINS)
+    totals = hist.sum(axis=0)
+    cum = np.concatenate([[0], np.cumsum(totals)])  # cum[b] = pairs with digit < b
+    N = int(cum[-1])
+    # boundary r (between rank r-1 and r) = the digit edge closest to r*N/P; edges are kept non-decreasing
+    edges = [0]
+    for r in range(1, P):
+        target = r * N / P
+        b = int(np.argmin(np.abs(cum - target)))
+        edges.append(max(b, edges[-1]))
+    edges.append(NUM_BINS)
+    bin_to_rank = np.zeros(NUM_BINS, dtype=np.uint8)
+    for r in range(P):
+        bin_to_rank[edges[r]:edges[r + 1]] = r
+    send_counts = np.zeros((P, P), dtype=np.int64)
+    for d in range(P):
+        send_counts[:, d] = hist[:, edges[d]:edges[d + 1]].sum(axis=1)
+    return {"bin_to_rank": bin_to_rank, "edges": edges, "send_counts": send_counts, "recv_total": send_counts.sum(axis=0), "total": N}
+
+
+class CudaLocalOps:
+    """The device side of the protocol on one B200, through the C ABI.  Buffers are torch int64 tensors (one
+    element = one {key, value} pair, key in the low half -- the AoS layout of Tahoe::uint2)."""
+
+    def __init__(self, device, pprims):
+        import torch
+        self.torch = torch
+        self.device, self.pprims = device, pprims
+        self.cuda = torch.device("cuda", device.device_idx)
+        self._hist = torch.zeros(NUM_BINS, dtype=torch.int64, device=self.cuda)
+        self._lut = torch.zeros(NUM_BINS, dtype=torch.uint8, device=self.cuda)
+        self._counts = torch.zeros(NUM_BINS, dtype=torch.int64, device=self.cuda)
+        self._temp = None
+
+    def empty(self, n):
+        return self.torch.empty(max(int(n), 1), dtype=self.torch.int64, device=self.cuda)
+
+    def histogram(self, pairs, n):
+        check(lib().b200rs_digit_histogram_pairs(self.device.handle, ctypes.c_void_p(pairs.data_ptr()), n, TOP_SHIFT, TOP_BITS,
+                                                 ctypes.c_void_p(self._hist.data_ptr())), "b200rs_digit_histogram_pairs")
+        return self._hist
+
+    def partition(self, src, dst, n, bin_to_part: np.ndarray, part_counts: np.ndarray):
+        t = self.torch
+        self._lut.copy_(t.from_numpy(np.ascontiguousarray(bin_to_part, dtype=np.uint8)), non_blocking=False)
+        counts = np.zeros(NUM_BINS, dtype=np.int64)
+        counts[: len(part_counts)] = part_counts
+        self._counts.copy_(t.from_numpy(counts), non_blocking=False)
+        need = ctypes.c_size_t(0)
+        fn = lib().b200rs_partition_pairs
+        check(fn(self.device.handle, None, None, n, TOP_SHIFT, TOP_BITS, None, None, None, ctypes.byref(need)), "b200rs_partition_pairs (size)")
+        if self._temp is None or self._temp.numel() < need.value:
+            self._temp = t.empty(need.value, dtype=t.uint8, device=self.cuda)
+        have = ctypes.c_size_t(self._temp.numel())
+        check(fn(self.device.handle, ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), n, TOP_SHIFT, TOP_BITS,
+                 ctypes.c_void_p(self._lut.data_ptr()), ctypes.c_void_p(self._counts.data_ptr()), ctypes.c_void_p(self._temp.data_ptr()),
+                 ctypes.byref(have)), "b200rs_partition_pairs")
+
+    def local_sort(self, pairs, m):
+        from .adl import PAIR_DTYPE, Buffer
+        self.pprims.radixSort(self.device, Buffer(self.device, m, PAIR_DTYPE, ptr=pairs.data_ptr()), m, 32)
+
+    def to_host_matrix(self, t):
+        return t.cpu().numpy()
+
+    def release(self):
+        self._temp = None
+
+
+class DistributedPairSorter:
+    """sort(pairs, n) -> (sorted_pairs_of_this_rank, m).  `pairs`: int64 tensor (or adl.Buffer of PAIR_DTYPE)
+    holding this rank's n input pairs; it is left unchanged.  The result is a view into an internal receive
+    buffer, valid until the next call."""
+
+    def __init__(self, device, pprims, capacity_pairs: int, dist, ops=None, slack: float = 1.25):
+        self.dist = dist
+        self.ops = ops if ops is not None else CudaLocalOps(device, pprims)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.capacity = int(capacity_pairs * slack) + 1024  # receive capacity; a plan that exceeds it raises
+        self.send = self.ops.empty(capacity_pairs)
+        self.recv = self.ops.empty(self.capacity)
+        self.last_plan = None
+
+    def _as_tensor(self, pairs, n):
+        if hasattr(pairs, "m_ptr"):  # adl.Buffer wrapping device memory: view it as int64 without copying
+            import torch
+            from .adl import PAIR_DTYPE
+            assert pairs.dtype == PAIR_DTYPE
+            return _tensor_from_ptr(torch, pairs.m_ptr, n, self.ops.cuda)
+        return pairs
+
+    def sort(self, pairs, n: int):
+        ops, dist = self.ops, self.dist
+        src = self._as_tensor(pairs, n)
+        hist = ops.histogram(src, n)
+        gathered = hist.new_empty(self.world * NUM_BINS)
+        dist.all_gather_into_tensor(gathered, hist)
+        plan = plan_exchange(ops.to_host_matrix(gathered).reshape(self.world, NUM_BINS))
+        self.last_plan = plan
+        m = int(plan["recv_total"][self.rank])
+        if int(plan["recv_total"].max()) > self.capacity:  # same decision on every rank: nobody enters the collective
+            raise B200RSError(ERR_CAPACITY, f"distributed sort: rank {int(plan['recv_total'].argmax())} would receive "
+                                            f"{int(plan['recv_total'].max())} pairs, capacity {self.capacity}")
+        send_counts = plan["send_counts"][self.rank]
+        ops.partition(src, self.send, n, plan["bin_to_rank"], send_counts)
+        recv_counts = plan["send_counts"][:, self.rank]
+        dist.all_to_all_single(self.recv[:m], self.send[:n], [int(c) for c in recv_counts], [int(c) for c in send_counts])
+        if m:
+            ops.local_sort(self.recv, m)
+        return self.recv[:m], m
+
+    def e2e(self, make_pairs, n: int, world: int):
+        """Same sort with HOST buffers: pinned host -> device, distributed sort, device -> pinned host, timed end to end."""
+        import time
+
+        import torch
+        host_in = make_pairs().view(torch.int64).reshape(-1).cpu().pin_memory()
+        host_out = torch.empty(self.capacity, dtype=torch.int64).pin_memory()
+        dev_in = self.ops.empty(n)
+        times = []
+        for _ in range(3):
+            self.dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dev_in.copy_(host_in, non_blocking=True)
+            out, m = self.sort(dev_in, n)
+            host_out[:m].copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self.dist.barrier()
+            times.append(time.perf_counter() - t0)
+        t = torch.tensor([min(times[1:])], device="cuda", dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        t = float(t.item())
+        return {"value": world * n / t / 1e9, "unit": "Gkeys/s", "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world,
+                "ms_per_step": 1e3 * t, "api": "DistributedPairSorter.sort with pinned host input/output per rank"}
+
+    def release(self):
+        self.send = self.recv = None
+        self.ops.release()
+
+
+def _tensor_from_ptr(torch, ptr: int, n: int, device):
+    """Zero-copy int64 view of `n` pairs at device address `ptr` (CUDA array interface)."""
+
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+    return torch.as_tensor(_Raw(), device=device)

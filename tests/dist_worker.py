@@ -1,0 +1,63 @@
+"""Worker for tests/test_gpu_dist.py: run under torchrun, one rank per GPU (NCCL).  Every rank generates its slice
+from (seed, rank), the partitioned sort runs, rank 0 gathers everything on the CPU and compares the rank-order
+concatenation with the oracle's stable sort of the concatenated input (bit-exact)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import oclradixsort_b200 as ob  # noqa: E402
+from oclradixsort_b200.dist import DistributedPairSorter  # noqa: E402
+
+
+def make_input(kind, rank, n):
+    rng = np.random.default_rng(7 + rank)
+    keys = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    if kind == "lowentropy":
+        keys = (keys & np.uint32(0x0F00000F)) * np.uint32(0x11)
+    elif kind == "skewtop":
+        keys = keys >> np.uint32(2 * rank)
+    kv = np.empty((n, 2), dtype=np.uint32)
+    kv[:, 0], kv[:, 1] = keys, np.arange(n, dtype=np.uint32) + np.uint32(rank << 26)
+    return kv
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = ob.DeviceUtils.allocate(ob.TYPE_CL, local, cuda_stream=torch.cuda.current_stream().cuda_stream)
+    pp = ob.Pprims()
+    ok = True
+    for kind, n in (("uniform", (1 << 20) + 17 * rank), ("lowentropy", 300_000), ("skewtop", 500_001)):
+        kv = make_input(kind, rank, n)
+        src = torch.from_numpy(kv.view(np.int64).reshape(-1).copy()).cuda()
+        sorter = DistributedPairSorter(dev, pp, n + 64, dist, slack=float(world) + 0.5)
+        out, m = sorter.sort(src, n)
+        torch.cuda.synchronize()
+        sizes = [None] * world
+        dist.all_gather_object(sizes, (n, m))
+        outs = [None] * world
+        dist.gather_object(out.cpu().numpy().view(np.uint32).reshape(m, 2), outs if rank == 0 else None, dst=0)
+        if rank == 0:
+            from oracle import pyoracle as po
+            whole = np.concatenate([make_input(kind, r, sizes[r][0]) for r in range(world)])
+            same = np.array_equal(np.concatenate(outs), po.sort_pairs(whole))
+            print(f"dist {kind}: per-rank in/out {sizes} bit-exact={same}", flush=True)
+            ok = ok and same
+        sorter.release()
+    pp.release()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,55 @@
+"""GPU tests of the multi-GPU sort: its single-GPU building blocks against numpy, and (when the box has >= 2 GPUs)
+the whole partitioned sort under torchrun + NCCL against the oracle."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_histogram_and_stable_partition_match_numpy():
+    import torch
+
+    import oclradixsort_b200 as ob
+    from oclradixsort_b200.dist import CudaLocalOps
+    d = ob.DeviceUtils.allocate(ob.TYPE_CL, 0, cuda_stream=torch.cuda.current_stream().cuda_stream)
+    p = ob.Pprims()
+    ops = CudaLocalOps(d, p)
+    rng = np.random.default_rng(3)
+    for n in (1, 6143, 6144, 6145, 1_000_003):
+        kv = np.empty((n, 2), dtype=np.uint32)
+        kv[:, 0] = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        kv[:, 1] = np.arange(n, dtype=np.uint32)
+        src = torch.from_numpy(kv.view(np.int64).reshape(-1).copy()).cuda()
+        hist = ops.histogram(src, n).cpu().numpy()
+        top = kv[:, 0] >> 24
+        assert np.array_equal(hist, np.bincount(top, minlength=256))
+        edges = np.sort(rng.integers(0, 257, size=7))
+        lut = np.searchsorted(edges, np.arange(256), side="right").astype(np.uint8)  # 8 contiguous parts, some may be empty
+        counts = np.bincount(lut[top], minlength=8)
+        dst = ops.empty(n)
+        ops.partition(src, dst, n, lut, counts)
+        torch.cuda.synchronize()
+        got = dst[:n].cpu().numpy().view(np.uint32).reshape(n, 2)
+        want = kv[np.argsort(lut[top], kind="stable")]
+        assert np.array_equal(got, want), n
+    ops.release()
+    p.release()
+    ob.DeviceUtils.deallocate(d)
+
+
+def test_partitioned_sort_two_gpus_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    world = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "dist_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
+    assert r.stdout.count("bit-exact=True") == 3, r.stdout[-2000:]
