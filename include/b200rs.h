@@ -119,6 +119,19 @@ int b200rs_partition_pairs(b200rs_device* dev, const b200rs_pair* in, b200rs_pai
                            const uint8_t* digit_to_part, const uint64_t* part_counts, void* temp, size_t* temp_bytes);
 
 /*
+ * Fused partition + exchange: like b200rs_partition_pairs, but part p is written starting at the absolute byte
+ * address part_base_addr[p] (device array, 256 x u64, 8-byte aligned addresses).  The addresses may belong to OTHER
+ * GPUs' buffers mapped with b200rs_ipc_import: the kernel then stores straight into peer memory over NVLink and
+ * no separate all-to-all is needed.  Elements of a part keep their input order.
+ */
+int b200rs_scatter_pairs_to_parts(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, int bits,
+                                  const uint8_t* digit_to_part, const uint64_t* part_base_addr, void* temp, size_t* temp_bytes);
+/* CUDA IPC for one-process-per-GPU jobs: export a b200rs_malloc'ed buffer, map a peer's buffer, unmap it. */
+int b200rs_ipc_export(b200rs_device* dev, void* ptr, unsigned char handle_out[64]);
+int b200rs_ipc_import(b200rs_device* dev, const unsigned char handle[64], void** ptr);
+int b200rs_ipc_release(b200rs_device* dev, void* ptr);
+
+/*
  * HOST-buffer forms: what a caller holding CPU arrays uses in place of the reference's
  * "getHostPtr / fill / returnHostPtr / radixSort / getHostPtr / read" sequence
  * (UnitTest/main.cpp:118-139).  Host -> device copy, sort/scan, device -> host copy, stream sync;

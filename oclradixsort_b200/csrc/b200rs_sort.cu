@@ -322,7 +322,10 @@ __device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT
 // LUT = true turns the pass into a stable PARTITION: the raw digit is mapped through digit_lut (256 bytes) to a part
 // id, ghist_pass holds the element count of every part, and the output is the parts laid out one after another in
 // part order.  Used by the multi-GPU sort to group elements by destination GPU (oclradixsort_b200/dist.py).
-template <typename ElemT, int THREADS, int IPT, int MODE, int MIN_CTAS, bool LUT = false>
+// ABS = true (with LUT): instead of one output array, every part p has its own absolute base address
+// ghist_pass[p] (bytes, 8-byte aligned) -- possibly in ANOTHER GPU's memory, mapped through CUDA IPC: the
+// partition and the exchange over NVLink are then one kernel (plain st.global to peer addresses).
+template <typename ElemT, int THREADS, int IPT, int MODE, int MIN_CTAS, bool LUT = false, bool ABS = false>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
                 const unsigned long long* __restrict__ ghist_pass /*[RADIX]*/, uint64_t* lookback /*[tiles][RADIX]*/,
@@ -358,13 +361,15 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
     // ---- 4. decoupled look-back, one thread per digit, LOOKBACK_WINDOW predecessors per step ----
     // The chain depth is (latency of one step) / (interval between tile starts): tens of tiles at full speed,
     // so each step fetches a window of predecessors with independent loads instead of one.
-    const bool wide = (n >> 32) != 0;  // element indices need 64 bits
+    const bool wide = ABS || (n >> 32) != 0;  // element indices need 64 bits
     if (tid < RADIX) {
         uint64_t exclusive = 0;
         if (tile == 0) {
-            // seed: global start of each digit = exclusive scan of the whole-input histogram
-            uint64_t* scratch = s.run_start;  // 8 x u64 of it, not yet in use
-            exclusive = block_exclusive_scan_256<uint64_t>((uint64_t)ghist_pass[tid], scratch, tid);
+            if (!ABS) {
+                // seed: global start of each digit = exclusive scan of the whole-input histogram
+                uint64_t* scratch = s.run_start;  // 8 x u64 of it, not yet in use
+                exclusive = block_exclusive_scan_256<uint64_t>((uint64_t)ghist_pass[tid], scratch, tid);
+            }  // ABS: every part starts at its own base address, the chain carries only this source's counts
         } else {
             const uint32_t tag_partial_hi = (tag_base + 1) << (LB_TAG_SHIFT - 32), tag_inclusive_hi = (tag_base + 2) << (LB_TAG_SHIFT - 32);
             const uint64_t* p = lookback + (uint64_t)(tile - 1) * RADIX + tid;  // tile 0 always publishes INCLUSIVE: the walk ends there
@@ -390,7 +395,8 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
             }
         }
         st_relaxed_u64(&lookback[(uint64_t)tile * RADIX + tid], TAG_INCLUSIVE | (exclusive + total));
-        s.run_start[tid] = exclusive - bin_start;  // out index of the element at tile-local slot j of digit d: run_start[d] + j
+        if (ABS) s.run_start[tid] = (uint64_t)ghist_pass[tid] + (exclusive - bin_start) * sizeof(ElemT);  // byte address of slot 0
+        else     s.run_start[tid] = exclusive - bin_start;  // out index of the element at tile-local slot j of digit d: run_start[d] + j
     }
     __syncthreads();
 
@@ -410,7 +416,8 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
             const ElemT e = s.staged[j];
             uint32_t d = (Elem<ElemT>::key(e) >> shift) & digit_mask;
             if (LUT) d = s.lut[d];
-            out[s.run_start[d] + j] = e;
+            if (ABS) *reinterpret_cast<ElemT*>(s.run_start[d] + (uint64_t)j * sizeof(ElemT)) = e;
+            else     out[s.run_start[d] + j] = e;
         }
     }
 }
@@ -633,6 +640,62 @@ extern "C" int b200rs_partition_pairs(b200rs_device* dev, const b200rs_pair* in,
                                                                      lookback, ticket, 0u, digit_to_part);
     }
     B200RS_CUDA(cudaGetLastError());
+    return B200RS_OK;
+}
+
+extern "C" int b200rs_scatter_pairs_to_parts(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, int bits,
+                                             const uint8_t* digit_to_part, const uint64_t* part_base_addr, void* temp, size_t* temp_bytes) {
+    using Cfg = OnesweepConfig<uint2, PART_THREADS, PART_IPT>;
+    if (!dev || !temp_bytes || shift < 0 || bits < 1 || bits > RADIX_BITS || shift + bits > 32) return B200RS_ERR_INVALID_ARGUMENT;
+    const uint64_t tiles = (n + Cfg::TILE - 1) / Cfg::TILE;
+    if (tiles > 0x7fffffffull) return B200RS_ERR_TOO_LARGE;
+    const size_t need = 256 + b200rs_align_up((size_t)tiles * RADIX * sizeof(uint64_t), 256);
+    if (!temp) {
+        *temp_bytes = need;
+        return B200RS_OK;
+    }
+    if (*temp_bytes < need) return B200RS_ERR_TEMP_TOO_SMALL;
+    if (n == 0) return B200RS_OK;
+    if (!in || !digit_to_part || !part_base_addr || ((uintptr_t)temp & 255u) || ((uintptr_t)in & 7u)) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    B200RS_CUDA(cudaMemsetAsync(temp, 0, need, dev->stream));
+    auto kernel = onesweep_kernel<uint2, PART_THREADS, PART_IPT, RANK_BALLOT, 3, true, true>;
+    const size_t smem = sizeof(typename Cfg::Smem);
+    B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(temp);
+    uint64_t* lookback = reinterpret_cast<uint64_t*>(static_cast<char*>(temp) + 256);
+    {
+        b200rs_launch_scope scope(dev, "scatter_pairs_to_parts", n, 2ull * n * sizeof(uint2));
+        kernel<<<(unsigned)tiles, PART_THREADS, smem, dev->stream>>>(reinterpret_cast<const uint2*>(in), nullptr, n, shift, (1u << bits) - 1u,
+                                                                     reinterpret_cast<const unsigned long long*>(part_base_addr), lookback, ticket,
+                                                                     0u, digit_to_part);
+    }
+    B200RS_CUDA(cudaGetLastError());
+    return B200RS_OK;
+}
+
+// ---- CUDA IPC: lets one-process-per-GPU ranks store into each other's buffers over NVLink ----
+extern "C" int b200rs_ipc_export(b200rs_device* dev, void* ptr, unsigned char handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!dev || !ptr || !handle_out) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    cudaIpcMemHandle_t h;
+    B200RS_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle_out, &h, 64);
+    return B200RS_OK;
+}
+extern "C" int b200rs_ipc_import(b200rs_device* dev, const unsigned char handle[64], void** ptr) {
+    if (!dev || !handle || !ptr) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    B200RS_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200RS_OK;
+}
+extern "C" int b200rs_ipc_release(b200rs_device* dev, void* ptr) {
+    if (!dev || !ptr) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    B200RS_CUDA(cudaIpcCloseMemHandle(ptr));
     return B200RS_OK;
 }
 

@@ -58,7 +58,18 @@ def plan_exchange(hist: np.ndarray) -> dict:
     send_counts = np.zeros((P, P), dtype=np.int64)
     for d in range(P):
         send_counts[:, d] = hist[:, edges[d]:edges[d + 1]].sum(axis=1)
-    return {"bin_to_rank": bin_to_rank, "edges": edges, "send_counts": send_counts, "recv_total": send_counts.sum(axis=0), "total": N}
+    # where source s writes inside destination d's receive buffer (pairs):
+    #   dest layout  [source 0 | source 1 | ...]                         recv_offset[s, d]
+    #   bins layout  [digit b0: source 0, source 1, ... | digit b0+1: ...]  bin_offset[s, b]
+    recv_offset = np.cumsum(send_counts, axis=0) - send_counts
+    bin_offset = np.zeros((P, NUM_BINS), dtype=np.int64)
+    for d in range(P):
+        lo, hi = edges[d], edges[d + 1]
+        digit_start = np.cumsum(totals[lo:hi]) - totals[lo:hi]          # start of each owned digit's block
+        within = np.cumsum(hist[:, lo:hi], axis=0) - hist[:, lo:hi]       # sources before s, same digit
+        bin_offset[:, lo:hi] = digit_start[None, :] + within
+    return {"bin_to_rank": bin_to_rank, "edges": edges, "send_counts": send_counts, "recv_total": send_counts.sum(axis=0), "total": N,
+            "recv_offset": recv_offset, "bin_offset": bin_offset}
 
 
 class CudaLocalOps:
@@ -103,6 +114,43 @@ class CudaLocalOps:
         from .adl import PAIR_DTYPE, Buffer
         self.pprims.radixSort(self.device, Buffer(self.device, m, PAIR_DTYPE, ptr=pairs.data_ptr()), m, 32)
 
+    # ---- peer-memory exchange (one process per GPU: CUDA IPC) ----
+    supports_p2p = True
+
+    def alloc_exported(self, n):
+        """(int64 tensor view, device address, 64-byte IPC handle) of a fresh cudaMalloc'ed buffer of n pairs."""
+        p = ctypes.c_void_p()
+        check(lib().b200rs_malloc(self.device.handle, int(n) * 8, ctypes.byref(p)), "b200rs_malloc")
+        handle = ctypes.create_string_buffer(64)
+        check(lib().b200rs_ipc_export(self.device.handle, p, handle), "b200rs_ipc_export")
+        return _tensor_from_ptr(self.torch, p.value, int(n), self.cuda), p.value, handle.raw
+
+    def import_peer(self, handle: bytes) -> int:
+        p = ctypes.c_void_p()
+        check(lib().b200rs_ipc_import(self.device.handle, handle, ctypes.byref(p)), "b200rs_ipc_import")
+        return p.value
+
+    def release_peer(self, addr: int):
+        check(lib().b200rs_ipc_release(self.device.handle, ctypes.c_void_p(addr)), "b200rs_ipc_release")
+
+    def free(self, addr: int):
+        check(lib().b200rs_free(self.device.handle, ctypes.c_void_p(addr)), "b200rs_free")
+
+    def scatter(self, src, n, digit_to_part: np.ndarray, part_base_addr: np.ndarray):
+        """Stable partition of src straight into the parts' base addresses (local or peer memory)."""
+        t = self.torch
+        self._lut.copy_(t.from_numpy(np.ascontiguousarray(digit_to_part, dtype=np.uint8)))
+        self._counts.copy_(t.from_numpy(np.ascontiguousarray(part_base_addr, dtype=np.uint64).view(np.int64)))
+        need = ctypes.c_size_t(0)
+        fn = lib().b200rs_scatter_pairs_to_parts
+        check(fn(self.device.handle, None, n, TOP_SHIFT, TOP_BITS, None, None, None, ctypes.byref(need)), "b200rs_scatter_pairs_to_parts (size)")
+        if self._temp is None or self._temp.numel() < need.value:
+            self._temp = t.empty(need.value, dtype=t.uint8, device=self.cuda)
+        have = ctypes.c_size_t(self._temp.numel())
+        check(fn(self.device.handle, ctypes.c_void_p(src.data_ptr()), n, TOP_SHIFT, TOP_BITS, ctypes.c_void_p(self._lut.data_ptr()),
+                 ctypes.c_void_p(self._counts.data_ptr()), ctypes.c_void_p(self._temp.data_ptr()), ctypes.byref(have)),
+              "b200rs_scatter_pairs_to_parts")
+
     def to_host_matrix(self, t):
         return t.cpu().numpy()
 
@@ -115,14 +163,32 @@ class DistributedPairSorter:
     holding this rank's n input pairs; it is left unchanged.  The result is a view into an internal receive
     buffer, valid until the next call."""
 
-    def __init__(self, device, pprims, capacity_pairs: int, dist, ops=None, slack: float = 1.25):
+    def __init__(self, device, pprims, capacity_pairs: int, dist, ops=None, slack: float = 1.25, exchange: str | None = None,
+                 layout: str = "dest"):
+        """exchange: "p2p"  -- ONE kernel partitions and stores straight into the destination GPUs' receive buffers
+                               (peer memory over NVLink, mapped with CUDA IPC); default on GPUs
+                     "nccl" -- partition into a local send buffer, then dist.all_to_all_single
+           layout (p2p only): "dest" = receive buffer ordered [source 0 | source 1 | ...];
+                              "bins" = ordered by top digit, then source (already grouped by the top digit)."""
         self.dist = dist
         self.ops = ops if ops is not None else CudaLocalOps(device, pprims)
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.capacity = int(capacity_pairs * slack) + 1024  # receive capacity; a plan that exceeds it raises
-        self.send = self.ops.empty(capacity_pairs)
-        self.recv = self.ops.empty(self.capacity)
+        self.exchange = exchange or ("p2p" if getattr(self.ops, "supports_p2p", False) else "nccl")
+        self.layout = layout
         self.last_plan = None
+        self.peers = None
+        if self.exchange == "p2p":
+            self.send = None
+            self.recv, self.recv_addr, handle = self.ops.alloc_exported(self.capacity)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle)
+            self.peers = [self.recv_addr if r == self.rank else self.ops.import_peer(handles[r]) for r in range(self.world)]
+            self._flag = self.ops.empty(1)
+            dist.barrier()
+        else:
+            self.send = self.ops.empty(capacity_pairs)
+            self.recv = self.ops.empty(self.capacity)
 
     def _as_tensor(self, pairs, n):
         if hasattr(pairs, "m_ptr"):  # adl.Buffer wrapping device memory: view it as int64 without copying
@@ -144,10 +210,24 @@ class DistributedPairSorter:
         if int(plan["recv_total"].max()) > self.capacity:  # same decision on every rank: nobody enters the collective
             raise B200RSError(ERR_CAPACITY, f"distributed sort: rank {int(plan['recv_total'].argmax())} would receive "
                                             f"{int(plan['recv_total'].max())} pairs, capacity {self.capacity}")
-        send_counts = plan["send_counts"][self.rank]
-        ops.partition(src, self.send, n, plan["bin_to_rank"], send_counts)
-        recv_counts = plan["send_counts"][:, self.rank]
-        dist.all_to_all_single(self.recv[:m], self.send[:n], [int(c) for c in recv_counts], [int(c) for c in send_counts])
+        if self.exchange == "p2p":
+            # The all-gather above doubles as the barrier that makes every rank's previous result dead before
+            # anyone overwrites a receive buffer.  One kernel: partition + stores into peer memory.
+            peers = np.asarray(self.peers, dtype=np.uint64)
+            base = np.zeros(NUM_BINS, dtype=np.uint64)
+            if self.layout == "bins":
+                lut = np.arange(NUM_BINS, dtype=np.uint8)
+                base[:] = peers[plan["bin_to_rank"]] + 8 * plan["bin_offset"][self.rank].astype(np.uint64)
+            else:
+                lut = plan["bin_to_rank"]
+                base[: self.world] = peers + 8 * plan["recv_offset"][self.rank].astype(np.uint64)
+            ops.scatter(src, n, lut, base)
+            dist.all_reduce(self._flag)  # every rank's stores have landed (kernel completion + collective) before anyone sorts
+        else:
+            send_counts = plan["send_counts"][self.rank]
+            ops.partition(src, self.send, n, plan["bin_to_rank"], send_counts)
+            recv_counts = plan["send_counts"][:, self.rank]
+            dist.all_to_all_single(self.recv[:m], self.send[:n], [int(c) for c in recv_counts], [int(c) for c in send_counts])
         if m:
             ops.local_sort(self.recv, m)
         return self.recv[:m], m
@@ -178,6 +258,16 @@ class DistributedPairSorter:
                 "ms_per_step": 1e3 * t, "api": "DistributedPairSorter.sort with pinned host input/output per rank"}
 
     def release(self):
+        if self.peers is not None:
+            import torch
+            torch.cuda.synchronize()
+            self.dist.barrier()  # nobody is still storing into a buffer that is about to be unmapped / freed
+            for r, addr in enumerate(self.peers):
+                if r != self.rank:
+                    self.ops.release_peer(addr)
+            self.recv = None
+            self.ops.free(self.recv_addr)
+            self.peers = None
         self.send = self.recv = None
         self.ops.release()
 

@@ -34,11 +34,15 @@ def main():
     dev = ob.DeviceUtils.allocate(ob.TYPE_CL, local, cuda_stream=torch.cuda.current_stream().cuda_stream)
     pp = ob.Pprims()
     ok = True
-    for kind, n in (("uniform", (1 << 20) + 17 * rank), ("lowentropy", 300_000), ("skewtop", 500_001)):
+    modes = [("nccl", "dest"), ("p2p", "dest"), ("p2p", "bins")]
+    cases = [("uniform", (1 << 20) + 17 * rank), ("lowentropy", 300_000), ("skewtop", 500_001)]
+    for (kind, n), (exchange, layout) in [(c, m) for c in cases for m in modes]:
         kv = make_input(kind, rank, n)
         src = torch.from_numpy(kv.view(np.int64).reshape(-1).copy()).cuda()
-        sorter = DistributedPairSorter(dev, pp, n + 64, dist, slack=float(world) + 0.5)
+        sorter = DistributedPairSorter(dev, pp, n + 64, dist, slack=float(world) + 0.5, exchange=exchange, layout=layout)
         out, m = sorter.sort(src, n)
+        out2, m2 = sorter.sort(src, n)  # a second call reuses the receive buffers
+        assert m2 == m
         torch.cuda.synchronize()
         sizes = [None] * world
         dist.all_gather_object(sizes, (n, m))
@@ -48,7 +52,7 @@ def main():
             from oracle import pyoracle as po
             whole = np.concatenate([make_input(kind, r, sizes[r][0]) for r in range(world)])
             same = np.array_equal(np.concatenate(outs), po.sort_pairs(whole))
-            print(f"dist {kind}: per-rank in/out {sizes} bit-exact={same}", flush=True)
+            print(f"dist {kind} {exchange}/{layout}: per-rank in/out {sizes} bit-exact={same}", flush=True)
             ok = ok and same
         sorter.release()
     pp.release()

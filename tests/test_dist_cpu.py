@@ -23,6 +23,13 @@ def test_plan_uniform_is_balanced_and_contiguous():
         assert (np.diff(b2r.astype(int)) >= 0).all() and b2r[0] == 0 and b2r[-1] == P - 1
         assert plan["send_counts"].sum() == hist.sum() and (plan["send_counts"].sum(axis=1) == hist.sum(axis=1)).all()
         assert plan["recv_total"].max() <= 1.05 * hist.sum() / P
+        # receive layouts tile every destination buffer exactly once
+        for d in range(P):
+            spans = sorted((int(plan["recv_offset"][s, d]), int(plan["send_counts"][s, d])) for s in range(P))
+            assert spans[0][0] == 0 and all(a + c == b for (a, c), (b, _) in zip(spans, spans[1:])) and sum(spans[-1]) == plan["recv_total"][d]
+            lo, hi = plan["edges"][d], plan["edges"][d + 1]
+            segs = sorted((int(plan["bin_offset"][s, b]), int(hist[s, b])) for s in range(P) for b in range(lo, hi))
+            assert segs[0][0] == 0 and all(a + c == b for (a, c), (b, _) in zip(segs, segs[1:])) and sum(segs[-1]) == plan["recv_total"][d]
 
 
 def test_plan_skewed_keeps_digit_ranges_whole():
@@ -81,7 +88,7 @@ def _worker(rank, world, port, kind, ns, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     n = ns[rank]
     kv = _make_input(kind, rank, n)
-    sorter = DistributedPairSorter(None, None, max(ns), dist, ops=NumpyOps(), slack=8.0)
+    sorter = DistributedPairSorter(None, None, max(ns), dist, ops=NumpyOps(), slack=8.0, exchange="nccl")
     out, m = sorter.sort(torch.from_numpy(kv.view(np.int64).reshape(-1).copy()), n)
     np.save(os.path.join(out_dir, f"out{rank}.npy"), out.numpy().view(np.uint32).reshape(m, 2))
     dist.barrier()
