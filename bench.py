@@ -217,6 +217,7 @@ def main() -> None:
 
         bufs = [fresh_pairs() for _ in range(nbuf)]
         handles = [ob.Buffer(dev, n, ob.PAIR_DTYPE, ptr=b.data_ptr()) for b in bufs]
+        inputs64 = [b.view(torch.int64).reshape(-1) for b in bufs]
 
         last = {}
 
@@ -224,7 +225,7 @@ def main() -> None:
             if sorter is None:
                 pp.radixSort(dev, handles[i], n, 32)
             else:
-                last["out"], last["m"] = sorter.sort(handles[i], n)
+                last["out"] = sorter.sort_async(inputs64[i], n)  # stream-ordered: no host round trip inside a step
 
         for i in range(args.warmup):
             step(i)
@@ -236,9 +237,11 @@ def main() -> None:
         sampler = ClockSampler(local_rank)
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         e0.record(stream)
         for i in range(args.warmup, nbuf):
             step(i)
+            marks[i - args.warmup].record(stream)  # per-step split times (reported, not used for `value`)
         e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
@@ -247,6 +250,7 @@ def main() -> None:
         clocks = sampler.stop()
         launches = dev.launch_count() - launches0
         ms = e0.elapsed_time(e1)
+        step_ms = [(e0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]) for k in range(args.steps)]
         if dist is not None:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -266,7 +270,8 @@ def main() -> None:
                 and int(v.to(torch.int64).sum().item()) == n * (n - 1) // 2
             del k64, same
         else:
-            out, m = last["out"], last["m"]
+            m = sorter.finish()  # element count of the last step (raises if a rank's share overflowed)
+            out = last["out"][:m]
             k64 = out & 0xFFFFFFFF  # key = low half of the 8-byte pair
             ok_local = bool((k64[1:] >= k64[:-1]).all()) if m > 1 else True
             lo = int(k64[0].item()) if m else 2**32
@@ -310,7 +315,7 @@ def main() -> None:
                                        "frac": 72 * n / (ms_per_step * 1e-3) / 1e9 / peak},
                         "histogram_kernel_ms": sum(e["ms"] for e in hist) / len(hist),
                         "scatter_share_of_step": sum(e["ms"] for e in scatter) / 3 / ms_per_step}
-        del bufs, handles
+        del bufs, handles, inputs64
 
         # ---- end to end through the C-ABI host-buffer entry point (pinned host memory) ----
         e2e = None
@@ -366,6 +371,7 @@ def main() -> None:
                        "pairs_per_gpu": n, "l2": "every step sorts a different 2 GiB buffer (inputs larger than L2, no flush needed)",
                        "parallelism": "single GPU" if world == 1 else f"msd-partitioned over {world} GPUs (histogram all-reduce + NVLink exchange + local LSD)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "step_ms_rank0": [round(x, 3) for x in step_ms],
         }
         if extras:
             line["extra"] = extras

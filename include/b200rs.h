@@ -125,7 +125,20 @@ int b200rs_partition_pairs(b200rs_device* dev, const b200rs_pair* in, b200rs_pai
  * no separate all-to-all is needed.  Elements of a part keep their input order.
  */
 int b200rs_scatter_pairs_to_parts(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, int bits,
-                                  const uint8_t* digit_to_part, const uint64_t* part_base_addr, void* temp, size_t* temp_bytes);
+                                  const uint8_t* digit_to_part, const uint64_t* part_base_addr, const uint64_t* n_dev /* optional: device-side
+                                  element count <= n (0 = do nothing) */, void* temp, size_t* temp_bytes);
+/*
+ * Exchange plan computed on the device, so the multi-GPU sort needs no host round trip: from the all-gathered
+ * top-digit histograms hist_all[world][256] it derives contiguous digit ranges per rank (about N/world pairs each),
+ * lut_out[256] (digit -> destination rank), part_base_out[256] (where THIS rank's pairs for destination d start:
+ * peer_base[d] + 8 * pairs sent to d by lower ranks), counts_out[0] = n_in (or 0 if aborted), counts_out[1] = pairs this
+ * rank will receive, status_out[0] = 1 if some rank's share exceeds `capacity` pairs (then nothing is exchanged).
+ */
+int b200rs_dist_plan(b200rs_device* dev, const uint64_t* hist_all, int world, int rank, const uint64_t* peer_base, uint64_t capacity,
+                     uint64_t n_in, uint8_t* lut_out, uint64_t* part_base_out, uint64_t* counts_out, uint32_t* status_out);
+/* b200rs_sort_pairs_u32 whose element count min(n_max, *n_dev) is read on the device (temp is sized for n_max). */
+int b200rs_sort_pairs_u32_devn(b200rs_device* dev, b200rs_pair* inout, uint64_t n_max, const uint64_t* n_dev, int sort_bits,
+                               void* temp, size_t* temp_bytes);
 /* CUDA IPC for one-process-per-GPU jobs: export a b200rs_malloc'ed buffer, map a peer's buffer, unmap it. */
 int b200rs_ipc_export(b200rs_device* dev, void* ptr, unsigned char handle_out[64]);
 int b200rs_ipc_import(b200rs_device* dev, const unsigned char handle[64], void** ptr);

@@ -63,8 +63,9 @@ constexpr int HIST_VEC_PER_THREAD = 4;  // uint4 loads in flight per thread
 template <typename ElemT>
 __global__ void __launch_bounds__(HIST_THREADS)
 digit_histogram_kernel(const ElemT* __restrict__ in, uint64_t n, int num_passes, uint32_t key_mask,
-                       unsigned long long* __restrict__ ghist /*[num_passes][RADIX]*/) {
+                       unsigned long long* __restrict__ ghist /*[num_passes][RADIX]*/, const unsigned long long* __restrict__ n_dev) {
     __shared__ uint32_t s_hist[MAX_PASSES][RADIX];
+    if (n_dev) n = min(n, (uint64_t)*n_dev);  // element count decided on the device (multi-GPU sort): n is only the upper bound
     for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += HIST_THREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
 
@@ -113,8 +114,9 @@ digit_histogram_kernel(const ElemT* __restrict__ in, uint64_t n, int num_passes,
 template <typename ElemT>
 __global__ void __launch_bounds__(HIST_THREADS)
 digit_histogram_unaligned_kernel(const ElemT* __restrict__ in, uint64_t n, int num_passes, uint32_t key_mask,
-                                 unsigned long long* __restrict__ ghist) {
+                                 unsigned long long* __restrict__ ghist, const unsigned long long* __restrict__ n_dev) {
     __shared__ uint32_t s_hist[MAX_PASSES][RADIX];
+    if (n_dev) n = min(n, (uint64_t)*n_dev);
     for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += HIST_THREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * HIST_THREADS;
@@ -329,9 +331,10 @@ template <typename ElemT, int THREADS, int IPT, int MODE, int MIN_CTAS, bool LUT
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
                 const unsigned long long* __restrict__ ghist_pass /*[RADIX]*/, uint64_t* lookback /*[tiles][RADIX]*/,
-                uint32_t* ticket, uint32_t tag_base, const uint8_t* __restrict__ digit_lut) {
+                uint32_t* ticket, uint32_t tag_base, const uint8_t* __restrict__ digit_lut, const unsigned long long* __restrict__ n_dev) {
     using Cfg = OnesweepConfig<ElemT, THREADS, IPT>;
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
+    if (n_dev) n = min(n, (uint64_t)*n_dev);  // device-decided element count; the grid was sized for the upper bound
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(smem_raw);
 
@@ -346,6 +349,7 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
     __syncthreads();
     const uint32_t tile = s.tile;
     const uint64_t tile_base = (uint64_t)tile * Cfg::TILE;
+    if (tile_base >= n) return;  // only when n came from n_dev: surplus CTAs of a grid sized for the upper bound
     const uint32_t valid = (uint32_t)min((uint64_t)Cfg::TILE, n - tile_base);  // elements of this tile that exist
     const bool byte_digit = !LUT && digit_mask == (uint32_t)(RADIX - 1);
     const uint32_t prmt_sel = 0x4440u | (uint32_t)(shift >> 3);
@@ -501,7 +505,8 @@ int make_plan(uint64_t n, int sort_bits, SortPlan* p) {
 }
 
 template <typename ElemT>
-int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes, const char* what) {
+int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes, const char* what,
+              const unsigned long long* n_dev = nullptr) {
     if (!dev || !temp_bytes) return B200RS_ERR_INVALID_ARGUMENT;
     SortPlan plan;
     B200RS_TRY(make_plan<ElemT>(n, sort_bits, &plan));
@@ -537,9 +542,9 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         const uint64_t max_blocks = (uint64_t)dev->num_sms * 4;  // 4 x 512 threads per SM, grid-stride beyond that
         if (blocks > max_blocks) blocks = max_blocks;
         if (((uintptr_t)inout & 15u) == 0)
-            digit_histogram_kernel<ElemT><<<(unsigned)blocks, HIST_THREADS, 0, dev->stream>>>(inout, n, plan.passes, key_mask, ghist);
+            digit_histogram_kernel<ElemT><<<(unsigned)blocks, HIST_THREADS, 0, dev->stream>>>(inout, n, plan.passes, key_mask, ghist, n_dev);
         else
-            digit_histogram_unaligned_kernel<ElemT><<<(unsigned)blocks, HIST_THREADS, 0, dev->stream>>>(inout, n, plan.passes, key_mask, ghist);
+            digit_histogram_unaligned_kernel<ElemT><<<(unsigned)blocks, HIST_THREADS, 0, dev->stream>>>(inout, n, plan.passes, key_mask, ghist, n_dev);
     }
     B200RS_CUDA(cudaGetLastError());
 
@@ -555,7 +560,7 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         uint32_t tag_base = (uint32_t)(2 * p);
         uint64_t n_arg = n;
         const uint8_t* no_lut = nullptr;
-        void* args[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lookback, &ticket, &tag_base, &no_lut};
+        void* args[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lookback, &ticket, &tag_base, &no_lut, &n_dev};
         snprintf(label, sizeof(label), "onesweep_%s_pass%d", what, p);
         {
             b200rs_launch_scope scope(dev, label, n, 2ull * n * sizeof(ElemT));
@@ -637,14 +642,15 @@ extern "C" int b200rs_partition_pairs(b200rs_device* dev, const b200rs_pair* in,
         b200rs_launch_scope scope(dev, "partition_pairs", n, 2ull * n * sizeof(uint2));
         kernel<<<(unsigned)tiles, PART_THREADS, smem, dev->stream>>>(reinterpret_cast<const uint2*>(in), reinterpret_cast<uint2*>(out), n, shift,
                                                                      (1u << bits) - 1u, reinterpret_cast<const unsigned long long*>(part_counts),
-                                                                     lookback, ticket, 0u, digit_to_part);
+                                                                     lookback, ticket, 0u, digit_to_part, nullptr);
     }
     B200RS_CUDA(cudaGetLastError());
     return B200RS_OK;
 }
 
 extern "C" int b200rs_scatter_pairs_to_parts(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, int bits,
-                                             const uint8_t* digit_to_part, const uint64_t* part_base_addr, void* temp, size_t* temp_bytes) {
+                                             const uint8_t* digit_to_part, const uint64_t* part_base_addr, const uint64_t* n_dev,
+                                             void* temp, size_t* temp_bytes) {
     using Cfg = OnesweepConfig<uint2, PART_THREADS, PART_IPT>;
     if (!dev || !temp_bytes || shift < 0 || bits < 1 || bits > RADIX_BITS || shift + bits > 32) return B200RS_ERR_INVALID_ARGUMENT;
     const uint64_t tiles = (n + Cfg::TILE - 1) / Cfg::TILE;
@@ -668,13 +674,120 @@ extern "C" int b200rs_scatter_pairs_to_parts(b200rs_device* dev, const b200rs_pa
         b200rs_launch_scope scope(dev, "scatter_pairs_to_parts", n, 2ull * n * sizeof(uint2));
         kernel<<<(unsigned)tiles, PART_THREADS, smem, dev->stream>>>(reinterpret_cast<const uint2*>(in), nullptr, n, shift, (1u << bits) - 1u,
                                                                      reinterpret_cast<const unsigned long long*>(part_base_addr), lookback, ticket,
-                                                                     0u, digit_to_part);
+                                                                     0u, digit_to_part, reinterpret_cast<const unsigned long long*>(n_dev));
     }
     B200RS_CUDA(cudaGetLastError());
     return B200RS_OK;
 }
 
+namespace {
+
+// ---- on-device exchange plan (one CTA of 256 threads): keeps the multi-GPU sort free of host round trips ----
+// hist_all[s][b] = pairs on source rank s with top digit b.  Digit ranges are contiguous per destination; the edge
+// between rank r-1 and r is the digit boundary whose cumulative count is closest to r*N/P (exact integer compare,
+// ties to the lower digit) -- the same rule as plan_exchange() in oclradixsort_b200/dist.py.
+__global__ void __launch_bounds__(RADIX)
+dist_plan_kernel(const unsigned long long* __restrict__ hist_all, int P, int me, const unsigned long long* __restrict__ peer_base,
+                 unsigned long long capacity, int n_in_valid, uint8_t* __restrict__ lut_out, unsigned long long* __restrict__ part_base_out,
+                 unsigned long long* __restrict__ counts_out /*[0]=n to scatter (0 when aborted), [1]=pairs this rank receives*/,
+                 uint32_t* __restrict__ status_out, unsigned long long n_in) {
+    __shared__ unsigned long long s_cum[RADIX + 1];
+    __shared__ unsigned long long s_scan[RADIX / 32];
+    __shared__ int s_edge[33];
+    __shared__ unsigned long long s_best[RADIX / 32];
+    __shared__ int s_best_b[RADIX / 32];
+    const int b = threadIdx.x, lane = b & 31, warp = b >> 5;
+    unsigned long long total = 0;
+    for (int s = 0; s < P; ++s) total += hist_all[(size_t)s * RADIX + b];
+    const unsigned long long excl = block_exclusive_scan_256<unsigned long long>(total, s_scan, b);
+    s_cum[b] = excl;
+    if (b == RADIX - 1) s_cum[RADIX] = excl + total;
+    if (b == 0) { s_edge[0] = 0; s_edge[P] = RADIX; }
+    __syncthreads();
+    const unsigned long long N = s_cum[RADIX];
+    for (int r = 1; r < P; ++r) {
+        // candidate boundaries 0..256: thread b evaluates b (and thread 255 also 256)
+        auto dist_to = [&](int edge) {
+            const unsigned long long a = s_cum[edge] * (unsigned long long)P, t = (unsigned long long)r * N;
+            return a > t ? a - t : t - a;
+        };
+        unsigned long long best = dist_to(b);
+        int best_b = b;
+        if (b == RADIX - 1 && dist_to(RADIX) < best) { best = dist_to(RADIX); best_b = RADIX; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ob = __shfl_down_sync(0xffffffffu, best, o);
+            const int obb = __shfl_down_sync(0xffffffffu, best_b, o);
+            if (ob < best || (ob == best && obb < best_b)) { best = ob; best_b = obb; }
+        }
+        if (lane == 0) { s_best[warp] = best; s_best_b[warp] = best_b; }
+        __syncthreads();
+        if (b == 0) {
+            for (int w = 1; w < RADIX / 32; ++w)
+                if (s_best[w] < best || (s_best[w] == best && s_best_b[w] < best_b)) { best = s_best[w]; best_b = s_best_b[w]; }
+            s_edge[r] = max(best_b, s_edge[r - 1]);
+        }
+        __syncthreads();
+    }
+    // owner of digit b
+    int owner = 0;
+    for (int r = 1; r < P; ++r) owner += (s_edge[r] <= b) ? 1 : 0;
+    lut_out[b] = (uint8_t)owner;
+    // part d (< P): pairs every source sends to d, my offset inside d's buffer, d's total
+    if (b < P) {
+        const int d = b;
+        unsigned long long before_me = 0, all = 0;
+        for (int s = 0; s < P; ++s) {
+            unsigned long long c = 0;
+            for (int k = s_edge[d]; k < s_edge[d + 1]; ++k) c += hist_all[(size_t)s * RADIX + k];
+            if (s < me) before_me += c;
+            all += c;
+        }
+        part_base_out[d] = peer_base[d] + 8ull * before_me;
+        s_cum[d] = all;  // reuse: total received by d
+    } else {
+        part_base_out[b] = 0;
+    }
+    __syncthreads();
+    if (b == 0) {
+        bool ok = true;
+        for (int d = 0; d < P; ++d) ok = ok && s_cum[d] <= capacity;
+        status_out[0] = ok ? 0u : 1u;           // 1 = some rank's share exceeds its receive capacity: nothing is exchanged
+        counts_out[0] = ok ? n_in : 0ull;
+        counts_out[1] = ok ? s_cum[me] : 0ull;
+    }
+    (void)n_in_valid;
+}
+
+}  // namespace
+
+extern "C" int b200rs_dist_plan(b200rs_device* dev, const uint64_t* hist_all, int world, int rank, const uint64_t* peer_base, uint64_t capacity,
+                                uint64_t n_in, uint8_t* lut_out, uint64_t* part_base_out, uint64_t* counts_out, uint32_t* status_out) {
+    if (!dev || !hist_all || !peer_base || !lut_out || !part_base_out || !counts_out || !status_out || world < 1 || world > 32 || rank < 0 || rank >= world)
+        return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    {
+        b200rs_launch_scope scope(dev, "dist_plan", (uint64_t)world * RADIX, (uint64_t)world * RADIX * 8);
+        dist_plan_kernel<<<1, RADIX, 0, dev->stream>>>(reinterpret_cast<const unsigned long long*>(hist_all), world, rank,
+                                                       reinterpret_cast<const unsigned long long*>(peer_base), capacity, 0, lut_out,
+                                                       reinterpret_cast<unsigned long long*>(part_base_out),
+                                                       reinterpret_cast<unsigned long long*>(counts_out), status_out, n_in);
+    }
+    B200RS_CUDA(cudaGetLastError());
+    return B200RS_OK;
+}
+
+extern "C" int b200rs_sort_pairs_u32_devn(b200rs_device* dev, b200rs_pair* inout, uint64_t n_max, const uint64_t* n_dev, int sort_bits,
+                                          void* temp, size_t* temp_bytes) {
+    return sort_impl<uint2>(dev, reinterpret_cast<uint2*>(inout), n_max, sort_bits, temp, temp_bytes, "pairs",
+                            reinterpret_cast<const unsigned long long*>(n_dev));
+}
+
+namespace {
+
 // ---- CUDA IPC: lets one-process-per-GPU ranks store into each other's buffers over NVLink ----
+}  // namespace
+
 extern "C" int b200rs_ipc_export(b200rs_device* dev, void* ptr, unsigned char handle_out[64]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     if (!dev || !ptr || !handle_out) return B200RS_ERR_INVALID_ARGUMENT;

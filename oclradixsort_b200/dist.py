@@ -45,11 +45,11 @@ def plan_exchange(hist: np.ndarray) -> dict:
     totals = hist.sum(axis=0)
     cum = np.concatenate([[0], np.cumsum(totals)])  # cum[b] = pairs with digit < b
     N = int(cum[-1])
-    # boundary r (between rank r-1 and r) = the digit edge closest to r*N/P; edges are kept non-decreasing
+    # boundary r (between rank r-1 and r) = the digit edge closest to r*N/P (exact integer compare, ties to the
+    # lower digit -- the same rule as dist_plan_kernel); edges are kept non-decreasing
     edges = [0]
     for r in range(1, P):
-        target = r * N / P
-        b = int(np.argmin(np.abs(cum - target)))
+        b = int(np.argmin(np.abs(cum * P - r * N)))
         edges.append(max(b, edges[-1]))
     edges.append(NUM_BINS)
     bin_to_rank = np.zeros(NUM_BINS, dtype=np.uint8)
@@ -136,6 +136,42 @@ class CudaLocalOps:
     def free(self, addr: int):
         check(lib().b200rs_free(self.device.handle, ctypes.c_void_p(addr)), "b200rs_free")
 
+    # ---- stream-ordered pipeline (no host round trip): plan, scatter and local sort all read device-side tables ----
+    def plan_async(self, gathered, world, rank, peers_dev, capacity, n):
+        t = self.torch
+        if not hasattr(self, "_cnts"):
+            self._cnts = t.zeros(2, dtype=t.int64, device=self.cuda)    # [0] pairs to scatter, [1] pairs received
+            self._status = t.zeros(1, dtype=t.int32, device=self.cuda)  # 1 = capacity exceeded, nothing exchanged
+        check(lib().b200rs_dist_plan(self.device.handle, ctypes.c_void_p(gathered.data_ptr()), world, rank, ctypes.c_void_p(peers_dev.data_ptr()),
+                                     capacity, n, ctypes.c_void_p(self._lut.data_ptr()), ctypes.c_void_p(self._counts.data_ptr()),
+                                     ctypes.c_void_p(self._cnts.data_ptr()), ctypes.c_void_p(self._status.data_ptr())), "b200rs_dist_plan")
+
+    def scatter_async(self, src, n):
+        t = self.torch
+        need = ctypes.c_size_t(0)
+        fn = lib().b200rs_scatter_pairs_to_parts
+        check(fn(self.device.handle, None, n, TOP_SHIFT, TOP_BITS, None, None, None, None, ctypes.byref(need)), "b200rs_scatter_pairs_to_parts (size)")
+        if self._temp is None or self._temp.numel() < need.value:
+            self._temp = t.empty(need.value, dtype=t.uint8, device=self.cuda)
+        have = ctypes.c_size_t(self._temp.numel())
+        check(fn(self.device.handle, ctypes.c_void_p(src.data_ptr()), n, TOP_SHIFT, TOP_BITS, ctypes.c_void_p(self._lut.data_ptr()),
+                 ctypes.c_void_p(self._counts.data_ptr()), ctypes.c_void_p(self._cnts.data_ptr()), ctypes.c_void_p(self._temp.data_ptr()),
+                 ctypes.byref(have)), "b200rs_scatter_pairs_to_parts")
+
+    def local_sort_devn(self, pairs, capacity):
+        need = ctypes.c_size_t(0)
+        fn = lib().b200rs_sort_pairs_u32_devn
+        check(fn(self.device.handle, None, capacity, None, 32, None, ctypes.byref(need)), "b200rs_sort_pairs_u32_devn (size)")
+        temp = self.pprims._scratch(self.device, need.value)
+        have = ctypes.c_size_t(temp.getSize())
+        check(fn(self.device.handle, ctypes.c_void_p(pairs.data_ptr()), capacity, ctypes.c_void_p(self._cnts.data_ptr() + 8), 32,
+                 ctypes.c_void_p(temp.m_ptr), ctypes.byref(have)), "b200rs_sort_pairs_u32_devn")
+
+    def read_counts(self):
+        """(pairs received, status) -- synchronises."""
+        c = self._cnts.cpu()
+        return int(c[1].item()), int(self._status.cpu().item())
+
     def scatter(self, src, n, digit_to_part: np.ndarray, part_base_addr: np.ndarray):
         """Stable partition of src straight into the parts' base addresses (local or peer memory)."""
         t = self.torch
@@ -143,12 +179,12 @@ class CudaLocalOps:
         self._counts.copy_(t.from_numpy(np.ascontiguousarray(part_base_addr, dtype=np.uint64).view(np.int64)))
         need = ctypes.c_size_t(0)
         fn = lib().b200rs_scatter_pairs_to_parts
-        check(fn(self.device.handle, None, n, TOP_SHIFT, TOP_BITS, None, None, None, ctypes.byref(need)), "b200rs_scatter_pairs_to_parts (size)")
+        check(fn(self.device.handle, None, n, TOP_SHIFT, TOP_BITS, None, None, None, None, ctypes.byref(need)), "b200rs_scatter_pairs_to_parts (size)")
         if self._temp is None or self._temp.numel() < need.value:
             self._temp = t.empty(need.value, dtype=t.uint8, device=self.cuda)
         have = ctypes.c_size_t(self._temp.numel())
         check(fn(self.device.handle, ctypes.c_void_p(src.data_ptr()), n, TOP_SHIFT, TOP_BITS, ctypes.c_void_p(self._lut.data_ptr()),
-                 ctypes.c_void_p(self._counts.data_ptr()), ctypes.c_void_p(self._temp.data_ptr()), ctypes.byref(have)),
+                 ctypes.c_void_p(self._counts.data_ptr()), None, ctypes.c_void_p(self._temp.data_ptr()), ctypes.byref(have)),
               "b200rs_scatter_pairs_to_parts")
 
     def to_host_matrix(self, t):
@@ -185,6 +221,8 @@ class DistributedPairSorter:
             dist.all_gather_object(handles, handle)
             self.peers = [self.recv_addr if r == self.rank else self.ops.import_peer(handles[r]) for r in range(self.world)]
             self._flag = self.ops.empty(1)
+            import torch
+            self._peers_dev = torch.tensor(self.peers, dtype=torch.int64, device=self.ops.cuda)
             dist.barrier()
         else:
             self.send = self.ops.empty(capacity_pairs)
@@ -198,7 +236,34 @@ class DistributedPairSorter:
             return _tensor_from_ptr(torch, pairs.m_ptr, n, self.ops.cuda)
         return pairs
 
+    def sort_async(self, pairs, n: int):
+        """p2p/dest only: enqueue the whole partitioned sort without any host round trip (histogram -> all-gather ->
+        on-device plan -> fused scatter into peer memory -> all-reduce barrier -> local sort with a device-side count).
+        Returns the receive buffer; call finish() for the element count (it synchronises and raises on overflow)."""
+        assert self.exchange == "p2p" and self.layout == "dest"
+        ops, dist = self.ops, self.dist
+        src = self._as_tensor(pairs, n)
+        hist = ops.histogram(src, n)
+        if not hasattr(self, "_gathered"):
+            self._gathered = hist.new_empty(self.world * NUM_BINS)
+        dist.all_gather_into_tensor(self._gathered, hist)  # also orders this step after every rank's previous local sort
+        ops.plan_async(self._gathered, self.world, self.rank, self._peers_dev, self.capacity, n)
+        ops.scatter_async(src, n)
+        dist.all_reduce(self._flag)  # every rank's stores have landed before anyone sorts
+        ops.local_sort_devn(self.recv, self.capacity)
+        return self.recv
+
+    def finish(self) -> int:
+        m, status = self.ops.read_counts()
+        if status != 0:
+            raise B200RSError(ERR_CAPACITY, f"distributed sort: a rank's share exceeds the receive capacity of {self.capacity} pairs")
+        return m
+
     def sort(self, pairs, n: int):
+        if self.exchange == "p2p" and self.layout == "dest" and hasattr(self.ops, "plan_async"):
+            out = self.sort_async(pairs, n)
+            m = self.finish()
+            return out[:m], m
         ops, dist = self.ops, self.dist
         src = self._as_tensor(pairs, n)
         hist = ops.histogram(src, n)
@@ -246,7 +311,7 @@ class DistributedPairSorter:
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             dev_in.copy_(host_in, non_blocking=True)
-            out, m = self.sort(dev_in, n)
+            out, m = self.sort(dev_in, n)  # finish() inside: the count is needed to size the copy back
             host_out[:m].copy_(out, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             self.dist.barrier()

@@ -43,6 +43,50 @@ def test_histogram_and_stable_partition_match_numpy():
     ob.DeviceUtils.deallocate(d)
 
 
+def test_device_plan_matches_host_plan():
+    import torch
+
+    import oclradixsort_b200 as ob
+    from oclradixsort_b200._lib import check, lib
+    from oclradixsort_b200.dist import plan_exchange
+    d = ob.DeviceUtils.allocate(ob.TYPE_CL, 0, cuda_stream=torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(11)
+    for P in (1, 2, 3, 8):
+        for kind in ("uniform", "skew", "onebin", "empty"):
+            hist = rng.integers(0, 5000, size=(P, 256)).astype(np.int64)
+            if kind == "skew":
+                hist[:, 10:20] *= 300
+            elif kind == "onebin":
+                hist[:] = 0
+                hist[:, 77] = 1234
+            elif kind == "empty":
+                hist[:] = 0
+            plan = plan_exchange(hist)
+            for me in range(P):
+                peers = np.arange(P, dtype=np.int64) * (1 << 40) + (1 << 30)
+                g = torch.from_numpy(hist.reshape(-1).copy()).cuda()
+                pd = torch.from_numpy(peers).cuda()
+                lut = torch.zeros(256, dtype=torch.uint8, device="cuda")
+                base = torch.zeros(256, dtype=torch.int64, device="cuda")
+                cnts = torch.zeros(2, dtype=torch.int64, device="cuda")
+                st = torch.ones(1, dtype=torch.int32, device="cuda")
+                cap = int(plan["recv_total"].max())
+                check(lib().b200rs_dist_plan(d.handle, ctypes.c_void_p(g.data_ptr()), P, me, ctypes.c_void_p(pd.data_ptr()), cap, 4242,
+                                             ctypes.c_void_p(lut.data_ptr()), ctypes.c_void_p(base.data_ptr()), ctypes.c_void_p(cnts.data_ptr()),
+                                             ctypes.c_void_p(st.data_ptr())), "b200rs_dist_plan")
+                torch.cuda.synchronize()
+                assert np.array_equal(lut.cpu().numpy(), plan["bin_to_rank"]), (P, kind)
+                assert np.array_equal(base.cpu().numpy()[:P], peers + 8 * plan["recv_offset"][me]), (P, kind, me)
+                assert cnts.cpu().tolist() == [4242, int(plan["recv_total"][me])] and int(st.item()) == 0
+                if cap > 0:  # one pair less capacity than needed: aborted, nothing to scatter or sort
+                    check(lib().b200rs_dist_plan(d.handle, ctypes.c_void_p(g.data_ptr()), P, me, ctypes.c_void_p(pd.data_ptr()), cap - 1, 4242,
+                                                 ctypes.c_void_p(lut.data_ptr()), ctypes.c_void_p(base.data_ptr()), ctypes.c_void_p(cnts.data_ptr()),
+                                                 ctypes.c_void_p(st.data_ptr())), "b200rs_dist_plan")
+                    torch.cuda.synchronize()
+                    assert cnts.cpu().tolist() == [0, 0] and int(st.item()) == 1
+    ob.DeviceUtils.deallocate(d)
+
+
 def test_partitioned_sort_two_gpus_nccl():
     import torch
     if torch.cuda.device_count() < 2:
