@@ -54,60 +54,103 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
+// shared-memory accesses through 32-bit shared-window addresses (keeps address arithmetic to one LEA)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void red_add_shared(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // =================================================================================================
 // Histogram of every digit in one read of the input.
 // =================================================================================================
 constexpr int HIST_THREADS = 512;
 constexpr int HIST_VEC_PER_THREAD = 4;  // uint4 loads in flight per thread
+constexpr int HIST_ROWS = RADIX / 2;    // two 16-bit counters per word: digits r (low half) and r + 128 (high half)
+constexpr int HIST_FLUSH_ROUNDS = 255;  // a counter half gains at most 16 warps x 16 keys = 256 per round: 255 rounds < 65536
+constexpr size_t HIST_SMEM_BYTES = (size_t)MAX_PASSES * HIST_ROWS * 32 * sizeof(uint32_t);  // 64 KiB
 
-template <typename ElemT>
+// Shared-memory atomics cost one L1 wavefront per lane that collides on a bank, and a random 8-bit digit makes
+// ~3.4 lanes of a warp collide: with one 256-bin table per digit place the round-1 kernel spent 27 SM-cycles per
+// 32 keys on its four RED.ADDs (ncu: L1/TEX 94 % busy, DRAM 30 %).  Here every lane owns a private column:
+// counter word (place p, row r, lane l) sits in bank l, so a warp's RED never conflicts.  A word packs two 16-bit
+// counters (digit r in the low half, digit r + 128 in the high half); the CTA drains the table into the global
+// 64-bit histogram before a half can overflow.
+template <typename ElemT, int NUM_PASSES>
 __global__ void __launch_bounds__(HIST_THREADS)
-digit_histogram_kernel(const ElemT* __restrict__ in, uint64_t n, int num_passes, uint32_t key_mask,
+digit_histogram_kernel(const ElemT* __restrict__ in, uint64_t n, uint32_t key_mask, uint32_t mul_0x101 /* 0x101, kept in a register */,
                        unsigned long long* __restrict__ ghist /*[num_passes][RADIX]*/, const unsigned long long* __restrict__ n_dev) {
-    __shared__ uint32_t s_hist[MAX_PASSES][RADIX];
+    extern __shared__ __align__(16) uint32_t s_cnt[];  // [MAX_PASSES][HIST_ROWS][32 lanes]
     if (n_dev) n = min(n, (uint64_t)*n_dev);  // element count decided on the device (multi-GPU sort): n is only the upper bound
-    for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += HIST_THREADS) (&s_hist[0][0])[i] = 0;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < MAX_PASSES * HIST_ROWS * 32; i += HIST_THREADS) s_cnt[i] = 0;
     __syncthreads();
 
     constexpr int KEYS_PER_VEC = 16 / sizeof(ElemT);  // 4 keys or 2 pairs per uint4
     const uint64_t nvec = n / KEYS_PER_VEC;
     const uint4* in4 = reinterpret_cast<const uint4*>(in);
+    const uint32_t table = smem_addr(s_cnt);  // warp-uniform
+    const uint32_t col = 4u * lane;           // this lane's column
 
+    constexpr int num_passes = NUM_PASSES;
     auto count = [&](uint32_t key) {
         key &= key_mask;
 #pragma unroll
-        for (int p = 0; p < MAX_PASSES; ++p)
-            if (p < num_passes) atomicAdd(&s_hist[p][(key >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+        for (int p = 0; p < NUM_PASSES; ++p) {
+                // row = low 7 bits of the digit, half = its top bit:  address = col + p*16K + row*128,
+                // increment = 1 << (16 * top bit) = 1 + 0xffff * top bit  (PRMT replicates the byte's sign bit)
+                uint32_t row_off;  // (shifted key & 0x3f80) | col in one LOP3
+                asm("lop3.b32 %0, %1, 0x3f80, %2, 0xea;" : "=r"(row_off) : "r"(p == 0 ? key << 7 : key >> (8 * p - 7)), "r"(col));
+                uint32_t top;  // 0xff if bit 7 of byte p is set, else 0 (prmt: selector bit 3 replicates the byte's sign)
+                asm("prmt.b32 %0, %1, 0, %2;" : "=r"(top) : "r"(key), "r"(0x4440u | (8u + p)));
+                red_add_shared(table + row_off + (uint32_t)p * (HIST_ROWS * 128u), top * mul_0x101 + 1u);
+        }
+    };
+    // drain: thread t owns row t of the [num_passes*128] rows; lanes read the row rotated so banks stay distinct
+    auto drain = [&]() {
+        __syncthreads();
+        if (tid < num_passes * HIST_ROWS) {
+            uint32_t lo = 0, hi = 0;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const int c = (j + tid) & 31;
+                const uint32_t w = s_cnt[tid * 32 + c];
+                s_cnt[tid * 32 + c] = 0;
+                lo += w & 0xffffu;
+                hi += w >> 16;
+            }
+            const int p = tid / HIST_ROWS, r = tid % HIST_ROWS;
+            if (lo) atomicAdd(&ghist[p * RADIX + r], (unsigned long long)lo);
+            if (hi) atomicAdd(&ghist[p * RADIX + r + HIST_ROWS], (unsigned long long)hi);
+        }
+        __syncthreads();
     };
 
-    const uint64_t stride = (uint64_t)gridDim.x * HIST_THREADS;
-    uint64_t v = (uint64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
-    // main loop: HIST_VEC_PER_THREAD independent 16-byte loads per thread before any use
-    for (; v + (HIST_VEC_PER_THREAD - 1) * stride < nvec; v += HIST_VEC_PER_THREAD * stride) {
+    // every thread of the CTA runs the same number of rounds (the bounds test is inside), so the drain's barriers are uniform
+    const uint64_t round_vecs = (uint64_t)HIST_THREADS * HIST_VEC_PER_THREAD;
+    int rounds = 0;
+    for (uint64_t base = (uint64_t)blockIdx.x * round_vecs; base < nvec; base += (uint64_t)gridDim.x * round_vecs) {
         uint4 q[HIST_VEC_PER_THREAD];
-#pragma unroll
-        for (int u = 0; u < HIST_VEC_PER_THREAD; ++u) q[u] = __ldg(in4 + v + u * stride);
+        bool have[HIST_VEC_PER_THREAD];
 #pragma unroll
         for (int u = 0; u < HIST_VEC_PER_THREAD; ++u) {
-            if (sizeof(ElemT) == 4) { count(q[u].x); count(q[u].y); count(q[u].z); count(q[u].w); }
-            else                    { count(q[u].x); count(q[u].z); }
+            const uint64_t v = base + (uint64_t)u * HIST_THREADS + tid;
+            have[u] = v < nvec;
+            if (have[u]) q[u] = __ldg(in4 + v);
         }
-    }
-    for (; v < nvec; v += stride) {
-        const uint4 q = __ldg(in4 + v);
-        if (sizeof(ElemT) == 4) { count(q.x); count(q.y); count(q.z); count(q.w); }
-        else                    { count(q.x); count(q.z); }
+#pragma unroll
+        for (int u = 0; u < HIST_VEC_PER_THREAD; ++u)
+            if (have[u]) {
+                if (sizeof(ElemT) == 4) { count(q[u].x); count(q[u].y); count(q[u].z); count(q[u].w); }
+                else                    { count(q[u].x); count(q[u].z); }
+            }
+        if (++rounds == HIST_FLUSH_ROUNDS) { drain(); rounds = 0; }
     }
     // ragged tail (n not a multiple of the vector width): block 0 only
     if (blockIdx.x == 0) {
-        const uint64_t i = nvec * KEYS_PER_VEC + threadIdx.x;
+        const uint64_t i = nvec * KEYS_PER_VEC + tid;
         if (i < n) count(Elem<ElemT>::key(in[i]));
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < num_passes * RADIX; i += HIST_THREADS) {
-        const uint32_t c = (&s_hist[0][0])[i];
-        if (c) atomicAdd(&ghist[i], (unsigned long long)c);
-    }
+    drain();
 }
 
 // Same, for inputs whose base pointer is not 16-byte aligned (element-wise loads).
@@ -136,7 +179,7 @@ digit_histogram_unaligned_kernel(const ElemT* __restrict__ in, uint64_t n, int n
 // =================================================================================================
 // One scatter pass.
 // =================================================================================================
-constexpr int LOOKBACK_WINDOW = 4;  // predecessors fetched per look-back step (independent loads in flight)
+constexpr int DEFAULT_LOOKBACK_WINDOW = 4;  // predecessors fetched per look-back step (independent loads in flight)
 constexpr uint64_t LB_VALUE_MASK = (1ull << 56) - 1;
 constexpr int LB_TAG_SHIFT = 56;
 
@@ -150,33 +193,40 @@ constexpr int LB_TAG_SHIFT = 56;
 //                 Exists to measure what the guaranteed ranking costs.
 enum RankMode { RANK_BALLOT = 0, RANK_MATCH = 1, RANK_ATOMIC_UNORDERED = 2 };
 
+// `minus_one` is 0xffffffff passed in as a kernel argument, i.e. a value ptxas cannot see: ~b is then computed as
+// b * minus_one + minus_one, an IMAD on the FMA pipe.  The obvious LOP3 form puts 16 logic operations per key on the
+// ALU pipe (one warp instruction per 2 cycles per scheduler), which is what bounded the round-1 kernel
+// (ncu: "math pipe throttle" + "not selected" = 37 % of the ranking samples).
 template <int MODE>
-__device__ __forceinline__ uint32_t same_digit_lanes(uint32_t digit) {
+__device__ __forceinline__ uint32_t same_digit_lanes(uint32_t digit, uint32_t minus_one) {
     if (MODE == RANK_MATCH) return __match_any_sync(0xffffffffu, digit);
-    uint32_t peers = 0xffffffffu;
-#pragma unroll
-    for (int k = 0; k < RADIX_BITS; ++k) {
-        uint32_t b;  // lanes whose bit k equals mine
+    // same_bit(k) = lanes whose bit k equals mine: ballot of the bit, complemented where my bit is clear
+    auto same_bit = [&](int k) {
+        uint32_t b;
         asm volatile(
             "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
             "and.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
-            "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t@!p not.b32 %0, %0;\n\t}"
+            "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t@!p mad.lo.u32 %0, %0, %3, %3;\n\t}"
             : "=r"(b)
-            : "r"(digit), "r"(1u << k));
-        peers &= b;
-    }
-    return peers;
+            : "r"(digit), "r"(1u << k), "r"(minus_one));
+        return b;
+    };
+    // three-input ANDs (4 LOP3 instead of 7), at most three ballots alive at a time
+    uint32_t peers, x, y;
+    peers = same_bit(0); x = same_bit(1); y = same_bit(2);
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x80;" : "+r"(peers) : "r"(x), "r"(y));
+    x = same_bit(3); y = same_bit(4);
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x80;" : "+r"(peers) : "r"(x), "r"(y));
+    x = same_bit(5); y = same_bit(6);
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x80;" : "+r"(peers) : "r"(x), "r"(y));
+    x = same_bit(7);
+    return peers & x;
 }
 
 __device__ __forceinline__ uint32_t lanemask_gt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
     return m;
-}
-// shared-memory accesses through 32-bit shared-window addresses (keeps address arithmetic to one LEA)
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void red_add_shared(uint32_t addr, uint32_t v) {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t atom_add_shared(uint32_t addr, uint32_t v) {
     uint32_t old;
@@ -257,7 +307,7 @@ template <typename ElemT, int THREADS, int IPT, int MODE, bool FULL, bool BYTE_D
 __device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem& s, const ElemT* __restrict__ in,
                                                    uint64_t tile_base, uint32_t valid, int shift, uint32_t digit_mask, uint32_t prmt_sel,
                                                    uint32_t tile, uint64_t* lookback, uint64_t tag_partial, uint32_t& total,
-                                                   uint32_t& bin_start) {
+                                                   uint32_t& bin_start, uint32_t minus_one) {
     using Cfg = OnesweepConfig<ElemT, THREADS, IPT>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t slice = warp * Cfg::WARP_SLICE + lane;  // tile-local index of item 0
@@ -308,15 +358,17 @@ __device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT
         if (MODE == RANK_ATOMIC_UNORDERED) {
             if (live) st_shared(staged + (uint32_t)sizeof(ElemT) * atom_add_shared(counter, 1u), elem[i]);
         } else {
-            uint32_t peers = same_digit_lanes<MODE>(digit);
+            uint32_t peers = same_digit_lanes<MODE>(digit, minus_one);
             if (!FULL) {
                 const uint32_t live_lanes = __ballot_sync(0xffffffffu, live);
                 peers = live ? (peers & live_lanes) : (1u << lane);  // padding lanes are nobody's peers
             }
-            // the highest lane of each group claims slots for the whole group
-            uint32_t slot = atom_add_shared_if(live && (peers & gt) == 0, counter, (uint32_t)__popc(peers));
+            // rank inside the group; the highest lane of each group claims slots for the whole group
+            // (its rank + 1 is the group size, so one POPC serves both)
+            const uint32_t rank = (uint32_t)__popc(peers & lt);
+            uint32_t slot = atom_add_shared_if(live && (peers & gt) == 0, counter, rank + 1u);
             slot = __shfl_sync(0xffffffffu, slot, 31 - __clz(peers));
-            if (live) st_shared(staged + (uint32_t)sizeof(ElemT) * (slot + __popc(peers & lt)), elem[i]);
+            if (live) st_shared(staged + (uint32_t)sizeof(ElemT) * rank + (uint32_t)sizeof(ElemT) * slot, elem[i]);
         }
     }
 }
@@ -327,11 +379,12 @@ __device__ __forceinline__ void count_rank_scatter(typename OnesweepConfig<ElemT
 // ABS = true (with LUT): instead of one output array, every part p has its own absolute base address
 // ghist_pass[p] (bytes, 8-byte aligned) -- possibly in ANOTHER GPU's memory, mapped through CUDA IPC: the
 // partition and the exchange over NVLink are then one kernel (plain st.global to peer addresses).
-template <typename ElemT, int THREADS, int IPT, int MODE, int MIN_CTAS, bool LUT = false, bool ABS = false>
+template <typename ElemT, int THREADS, int IPT, int MODE, int MIN_CTAS, bool LUT = false, bool ABS = false, int LOOKBACK_WINDOW = DEFAULT_LOOKBACK_WINDOW>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
                 const unsigned long long* __restrict__ ghist_pass /*[RADIX]*/, uint64_t* lookback /*[tiles][RADIX]*/,
-                uint32_t* ticket, uint32_t tag_base, const uint8_t* __restrict__ digit_lut, const unsigned long long* __restrict__ n_dev) {
+                uint32_t* ticket, uint32_t tag_base, const uint8_t* __restrict__ digit_lut, const unsigned long long* __restrict__ n_dev,
+                uint32_t minus_one /* 0xffffffff, opaque to ptxas: see same_digit_lanes */) {
     using Cfg = OnesweepConfig<ElemT, THREADS, IPT>;
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
     if (n_dev) n = min(n, (uint64_t)*n_dev);  // device-decided element count; the grid was sized for the upper bound
@@ -356,10 +409,10 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
 
     uint32_t total = 0, bin_start = 0;  // meaningful in the 256 digit threads
     if (valid == Cfg::TILE) {
-        if (byte_digit) count_rank_scatter<ElemT, THREADS, IPT, MODE, true, !LUT, LUT>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
-        else            count_rank_scatter<ElemT, THREADS, IPT, MODE, true, false, LUT>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
+        if (byte_digit) count_rank_scatter<ElemT, THREADS, IPT, MODE, true, !LUT, LUT>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start, minus_one);
+        else            count_rank_scatter<ElemT, THREADS, IPT, MODE, true, false, LUT>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start, minus_one);
     } else {
-        count_rank_scatter<ElemT, THREADS, IPT, MODE, false, false, LUT>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start);
+        count_rank_scatter<ElemT, THREADS, IPT, MODE, false, false, LUT>(s, in, tile_base, valid, shift, digit_mask, prmt_sel, tile, lookback, TAG_PARTIAL, total, bin_start, minus_one);
     }
 
     // ---- 4. decoupled look-back, one thread per digit, LOOKBACK_WINDOW predecessors per step ----
@@ -437,6 +490,8 @@ struct Variant {
 };
 #define B200RS_VARIANT(ElemT, THREADS, IPT, MODE, MIN_CTAS) \
     Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS}
+#define B200RS_VARIANT_W(ElemT, THREADS, IPT, MODE, MIN_CTAS, W) \
+    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS, false, false, W>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS "w" #W}
 
 template <typename ElemT> struct Variants;
 template <> struct Variants<uint32_t> {
@@ -449,6 +504,10 @@ template <> struct Variants<uint32_t> {
             B200RS_VARIANT(uint32_t, 1024, 16, RANK_BALLOT, 1),
             B200RS_VARIANT(uint32_t, 512, 16, RANK_MATCH, 3),             // measurement only
             B200RS_VARIANT(uint32_t, 512, 20, RANK_ATOMIC_UNORDERED, 3),  // measurement only, not stable by contract
+            B200RS_VARIANT_W(uint32_t, 512, 24, RANK_BALLOT, 3, 8),   // 7
+            B200RS_VARIANT_W(uint32_t, 512, 24, RANK_BALLOT, 3, 16),  // 8
+            B200RS_VARIANT_W(uint32_t, 512, 24, RANK_BALLOT, 3, 2),   // 9
+            B200RS_VARIANT_W(uint32_t, 512, 24, RANK_BALLOT, 3, 1),   // 10
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
@@ -463,6 +522,9 @@ template <> struct Variants<uint2> {
             B200RS_VARIANT(uint2, 512, 12, RANK_BALLOT, 3),
             B200RS_VARIANT(uint2, 1024, 12, RANK_BALLOT, 1),
             B200RS_VARIANT(uint2, 512, 16, RANK_ATOMIC_UNORDERED, 2),  // measurement only, not stable by contract
+            B200RS_VARIANT_W(uint2, 384, 16, RANK_BALLOT, 3, 8),   // 5
+            B200RS_VARIANT_W(uint2, 384, 16, RANK_BALLOT, 3, 16),  // 6
+            B200RS_VARIANT_W(uint2, 384, 16, RANK_BALLOT, 3, 2),   // 7
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
@@ -539,12 +601,18 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         b200rs_launch_scope scope(dev, label, n, n * sizeof(ElemT));
         const uint64_t per_block = (uint64_t)HIST_THREADS * HIST_VEC_PER_THREAD * (16 / sizeof(ElemT));
         uint64_t blocks = (n + per_block - 1) / per_block;
-        const uint64_t max_blocks = (uint64_t)dev->num_sms * 4;  // 4 x 512 threads per SM, grid-stride beyond that
-        if (blocks > max_blocks) blocks = max_blocks;
-        if (((uintptr_t)inout & 15u) == 0)
-            digit_histogram_kernel<ElemT><<<(unsigned)blocks, HIST_THREADS, 0, dev->stream>>>(inout, n, plan.passes, key_mask, ghist, n_dev);
-        else
+        if (((uintptr_t)inout & 15u) == 0) {
+            const uint64_t max_blocks = (uint64_t)dev->num_sms * 3;  // 3 x (512 threads, 64 KiB of counters) per SM, grid-stride beyond that
+            if (blocks > max_blocks) blocks = max_blocks;
+            auto kernel = plan.passes == 4 ? digit_histogram_kernel<ElemT, 4> : plan.passes == 3 ? digit_histogram_kernel<ElemT, 3>
+                        : plan.passes == 2 ? digit_histogram_kernel<ElemT, 2> : digit_histogram_kernel<ElemT, 1>;
+            B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HIST_SMEM_BYTES));
+            kernel<<<(unsigned)blocks, HIST_THREADS, HIST_SMEM_BYTES, dev->stream>>>(inout, n, key_mask, 0x101u, ghist, n_dev);
+        } else {
+            const uint64_t max_blocks = (uint64_t)dev->num_sms * 4;
+            if (blocks > max_blocks) blocks = max_blocks;
             digit_histogram_unaligned_kernel<ElemT><<<(unsigned)blocks, HIST_THREADS, 0, dev->stream>>>(inout, n, plan.passes, key_mask, ghist, n_dev);
+        }
     }
     B200RS_CUDA(cudaGetLastError());
 
@@ -560,7 +628,8 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         uint32_t tag_base = (uint32_t)(2 * p);
         uint64_t n_arg = n;
         const uint8_t* no_lut = nullptr;
-        void* args[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lookback, &ticket, &tag_base, &no_lut, &n_dev};
+        uint32_t minus_one = 0xffffffffu;
+        void* args[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lookback, &ticket, &tag_base, &no_lut, &n_dev, &minus_one};
         snprintf(label, sizeof(label), "onesweep_%s_pass%d", what, p);
         {
             b200rs_launch_scope scope(dev, label, n, 2ull * n * sizeof(ElemT));
@@ -642,7 +711,7 @@ extern "C" int b200rs_partition_pairs(b200rs_device* dev, const b200rs_pair* in,
         b200rs_launch_scope scope(dev, "partition_pairs", n, 2ull * n * sizeof(uint2));
         kernel<<<(unsigned)tiles, PART_THREADS, smem, dev->stream>>>(reinterpret_cast<const uint2*>(in), reinterpret_cast<uint2*>(out), n, shift,
                                                                      (1u << bits) - 1u, reinterpret_cast<const unsigned long long*>(part_counts),
-                                                                     lookback, ticket, 0u, digit_to_part, nullptr);
+                                                                     lookback, ticket, 0u, digit_to_part, nullptr, 0xffffffffu);
     }
     B200RS_CUDA(cudaGetLastError());
     return B200RS_OK;
@@ -674,7 +743,7 @@ extern "C" int b200rs_scatter_pairs_to_parts(b200rs_device* dev, const b200rs_pa
         b200rs_launch_scope scope(dev, "scatter_pairs_to_parts", n, 2ull * n * sizeof(uint2));
         kernel<<<(unsigned)tiles, PART_THREADS, smem, dev->stream>>>(reinterpret_cast<const uint2*>(in), nullptr, n, shift, (1u << bits) - 1u,
                                                                      reinterpret_cast<const unsigned long long*>(part_base_addr), lookback, ticket,
-                                                                     0u, digit_to_part, reinterpret_cast<const unsigned long long*>(n_dev));
+                                                                     0u, digit_to_part, reinterpret_cast<const unsigned long long*>(n_dev), 0xffffffffu);
     }
     B200RS_CUDA(cudaGetLastError());
     return B200RS_OK;
