@@ -1,0 +1,298 @@
+// b200rs_onesweep2.cuh -- second-generation scatter pass (included by b200rs_sort.cu, inside its anonymous namespace).
+//
+// Same contract as onesweep_kernel (one stable scatter pass on an 8-bit digit; replaces SortAndScatterKernel /
+// SortAndScatterKeyValueKernel, RadixSort32Kernels.cl:495-631, RadixSortKeyValueKernels.cl:513-663).  What the profile of
+// onesweep_kernel showed (profiles/r1_*, gpurun session 3): per 32 pairs 82 warp instructions, of which 16.7 were the
+// per-digit tagged look-back walk (5 iterations x 73 instructions per digit thread per tile: at B200 speed a tile
+// completes every 50-100 ns, so the nearest tile with an inclusive prefix is 20-80 tiles back) and 10.7 the element-wise
+// write-out; L1/TEX data pipe 77 % busy.  Here:
+//
+//   * TWO-LEVEL decoupled look-back.  Tiles form groups of LB_GROUP.  Every tile publishes its digit counts (u32 words
+//     {tag:4 | count:28}); the last tile of a group adds up its group's counts and publishes the GROUP aggregate, later
+//     the group's inclusive prefix, in one tagged u64 word per digit -- the classic single-word protocol, but at group
+//     granularity, so the chain is LB_GROUP times shorter.  A tile's prefix = digit start (pre-scanned histogram) +
+//     group chain (window of 4 independent loads per step) + counts of the tiles before it in its own group (at most
+//     LB_GROUP-1 independent loads).  No fences anywhere: every word validates itself through its tag.
+//   * ORDER_EARLY: the look-back runs BEFORE the ranking phase, so the global position of every digit's run is known
+//     when the tile-local layout is decided: each run is placed in shared memory at the same offset modulo 16 bytes as
+//     its destination in global memory, and the write-out is one cp.async.bulk (TMA, shared -> global) per digit for the
+//     16-byte-aligned body of its run plus at most (16/sizeof(elem) - 1) element stores at each ragged end.
+//   * ORDER_LATE: look-back after the ranking phase (its latency hides behind the ranking of the other resident CTAs),
+//     element-wise write-out with per-digit 64-bit base pointers.
+#pragma once
+
+enum WriteOut { WO_ELEM = 0, WO_BULK = 1 };
+enum LookbackOrder { ORDER_LATE = 0, ORDER_EARLY = 1 };
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename ElemT, int THREADS, int IPT, int WO>
+struct Onesweep2Config {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * IPT;
+    static constexpr int WARP_SLICE = 32 * IPT;
+    static constexpr int M = WO == WO_BULK ? 16 / (int)sizeof(ElemT) : 1;         // elements per 16-byte chunk
+    static constexpr int STAGE_SLOTS = TILE + (M > 1 ? 2 * (M - 1) * RADIX : 0);  // every run may be padded at both ends
+    struct Smem {
+        alignas(16) ElemT staged[STAGE_SLOTS];  // tile in sorted order; run d starts at a slot congruent to its global index mod M
+        uint32_t warp_offset[WARPS][RADIX];     // per-warp digit counts -> running staged slot of (warp, digit)
+        uint64_t run_ptr[RADIX];                // WO_ELEM: byte address in `out` of staged slot 0, as seen by digit d's run
+        uint64_t scan_scratch[RADIX / 32];
+        uint32_t dummy[32];                     // lanes that are not their group's leader aim their atomic here (bank = lane)
+        uint32_t tile;
+    };
+};
+
+// Look-back table (both arrays zeroed by the host once per sort; tags differ per pass):
+//   partial[tile][256]  u32  {tag:4 = 2*pass + 1 | elements of the tile with this digit : 28}
+//   group[tile / LB_GROUP][256] u64 {tag:8 | value:56}
+//        tag 2*pass + 1: value = elements of the group's tiles with this digit
+//        tag 2*pass + 2: value = elements of tiles 0 .. last tile of the group with this digit
+constexpr int LB_GROUP = 8;
+constexpr int LB2_PARTIAL_SHIFT = 28;
+struct Lookback3 {
+    uint32_t* partial;
+    uint64_t* group;
+};
+
+// Sum of `count` (< LB_GROUP, CTA-uniform) consecutive tiles' counts of one digit; spins until every word carries `tag`.
+__device__ __forceinline__ uint32_t sum_tile_partials(const uint32_t* p, uint32_t count, uint32_t tag) {
+    uint32_t sum;
+    while (true) {
+        sum = 0;
+        uint32_t bad = 0;
+#pragma unroll
+        for (int j = 0; j < LB_GROUP - 1; ++j)
+            if ((uint32_t)j < count) {
+                const uint32_t x = ld_relaxed_u32(p + j * RADIX) ^ tag;  // the count if the tag matches, >= 2^28 otherwise
+                sum += x;
+                bad |= x;
+            }
+        if ((bad >> LB2_PARTIAL_SHIFT) == 0) break;
+    }
+    return sum;
+}
+
+// Early half, digit threads, right after the tile's digit totals are known: publish them; the last tile of a group
+// also publishes the group aggregate (it needs its group-mates' counts for that, and keeps their sum).
+__device__ __forceinline__ uint32_t lookback3_publish(const Lookback3& lb, uint32_t tile, uint32_t pass, uint32_t total, int tid) {
+    const uint32_t tag_partial = (2u * pass + 1u) << LB2_PARTIAL_SHIFT;
+    st_relaxed_u32(&lb.partial[(uint64_t)tile * RADIX + tid], tag_partial | total);
+    const uint32_t q = tile % LB_GROUP;
+    uint32_t mates = 0;
+    if (q == LB_GROUP - 1) {
+        mates = sum_tile_partials(lb.partial + (uint64_t)(tile - q) * RADIX + tid, q, tag_partial);
+        st_relaxed_u64(&lb.group[(uint64_t)(tile / LB_GROUP) * RADIX + tid], ((uint64_t)(2u * pass + 1u) << LB_TAG_SHIFT) | (uint64_t)(mates + total));
+    }
+    return mates;
+}
+
+// Late half: returns the number of elements with this digit in tiles 0 .. tile-1.
+__device__ __forceinline__ uint64_t lookback3_resolve(const Lookback3& lb, uint32_t tile, uint32_t pass, uint32_t total, uint32_t mates, int tid) {
+    const uint32_t q = tile % LB_GROUP, g = tile / LB_GROUP;
+    if (q != LB_GROUP - 1) mates = sum_tile_partials(lb.partial + (uint64_t)(tile - q) * RADIX + tid, q, (2u * pass + 1u) << LB2_PARTIAL_SHIFT);
+    uint64_t acc = 0;
+    const uint32_t tag_aggregate_hi = (2u * pass + 1u) << (LB_TAG_SHIFT - 32);
+    const uint64_t end_of_chain = (uint64_t)(2u * pass + 2u) << LB_TAG_SHIFT;  // "inclusive prefix 0": what lies below group 0
+    int32_t h = (int32_t)g - 1;                                                  // nearest group not yet accounted for
+    const uint64_t* p = lb.group + (int64_t)h * RADIX + tid;                     // not dereferenced when h < 0
+    bool done = h < 0;
+    while (!done) {
+        uint64_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = j <= h ? ld_relaxed_u64(p - j * RADIX) : end_of_chain;
+        bool open = true;  // entries are consumed in order, up to the first one that is not published or is inclusive
+        int32_t consumed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t t = (uint32_t)(w[j] >> 32) - tag_aggregate_hi;  // aggregate: [0, 2^24), inclusive: [2^24, 2^25)
+            const bool take = open && t < (2u << (LB_TAG_SHIFT - 32));
+            const bool inclusive = t >= (1u << (LB_TAG_SHIFT - 32));
+            if (take) {
+                acc += w[j] & LB_VALUE_MASK;
+                ++consumed;
+            }
+            done = done || (take && inclusive);
+            open = take && !inclusive;
+        }
+        p -= consumed * RADIX;
+        h -= consumed;
+    }
+    if (q == LB_GROUP - 1) st_relaxed_u64(&lb.group[(uint64_t)g * RADIX + tid], ((uint64_t)(2u * pass + 2u) << LB_TAG_SHIFT) | (acc + mates + total));
+    return acc + mates;
+}
+
+__device__ __forceinline__ void bulk_copy_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t lanemask_le() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}
+
+template <typename ElemT, int THREADS, int IPT, int WO, int ORDER, bool FULL, bool BYTE_DIGIT>
+__device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, THREADS, IPT, WO>::Smem& s, const ElemT* __restrict__ in,
+                                               ElemT* __restrict__ out, uint64_t tile_base, uint32_t valid, int shift,
+                                               uint32_t digit_mask, uint32_t prmt_sel, uint32_t tile, uint32_t pass,
+                                               const unsigned long long* __restrict__ digit_start, const Lookback3& lb, uint32_t minus_one) {
+    using Cfg = Onesweep2Config<ElemT, THREADS, IPT, WO>;
+    constexpr int M = Cfg::M;
+    constexpr uint32_t E = (uint32_t)sizeof(ElemT);
+    static_assert(WO == WO_ELEM || ORDER == ORDER_EARLY, "the bulk write-out needs the global positions before the tile is laid out");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t slice = warp * Cfg::WARP_SLICE + lane;  // tile-local index of item 0
+    const uint32_t my_offset = smem_addr(&s.warp_offset[warp][0]);
+    const uint32_t staged = smem_addr(&s.staged[0]);
+
+    // ---- 1. warp-striped load + per-warp digit counts ----
+    ElemT elem[IPT];
+    const ElemT* __restrict__ src = in + tile_base + slice;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+        if (FULL || slice + i * 32 < valid) elem[i] = src[i * 32];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+        if (FULL || slice + i * 32 < valid) {
+            const uint32_t d = digit_of_opaque<BYTE_DIGIT>(Elem<ElemT>::key(elem[i]), shift, digit_mask, prmt_sel);
+            red_add_shared(my_offset + 4u * d, 1u);
+        }
+    __syncthreads();
+
+    // ---- 2. one thread per digit: tile totals, publication, (ORDER_EARLY: look-back,) layout of the staged tile ----
+    uint32_t total = 0, sbase = 0, mates = 0;  // digit threads: elements of digit tid in this tile, staged slot of the first one
+    uint64_t exclusive = 0;                    // digit threads: global index of the first one
+    if (tid < RADIX) {
+#pragma unroll
+        for (int w = 0; w < Cfg::WARPS; ++w) total += s.warp_offset[w][tid];
+        mates = lookback3_publish(lb, tile, pass, total, tid);
+        uint32_t a = 0, region = total;
+        if (ORDER == ORDER_EARLY) {
+            exclusive = (uint64_t)digit_start[tid] + lookback3_resolve(lb, tile, pass, total, mates, tid);
+            if (M > 1) {
+                a = (uint32_t)(((uintptr_t)out / sizeof(ElemT) + exclusive) & (uint64_t)(M - 1));  // position inside its 16-byte chunk
+                region = total ? ((a + total + (uint32_t)(M - 1)) & ~(uint32_t)(M - 1)) : 0u;
+            }
+        }
+        sbase = block_exclusive_scan_256<uint32_t>(region, reinterpret_cast<uint32_t*>(s.scan_scratch), tid) + a;
+        // the running slot of (warp, digit) is kept as a shared-memory BYTE address biased by one element, so that the
+        // ranking loop adds E * (lanes of the group up to and including me) and stores without any further arithmetic
+        uint32_t run = staged + E * sbase - E;
+#pragma unroll
+        for (int w = 0; w < Cfg::WARPS; ++w) {
+            const uint32_t c = s.warp_offset[w][tid];
+            s.warp_offset[w][tid] = run;
+            run += E * c;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. warp multisplit ranking; each element goes straight to its staged slot ----
+    const uint32_t le = lanemask_le(), gt = lanemask_gt();
+    const uint32_t dummy = smem_addr(&s.dummy[lane]);
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+        const bool live = FULL || (slice + i * 32 < valid);
+        const uint32_t digit = live ? digit_of<BYTE_DIGIT>(Elem<ElemT>::key(elem[i]), shift, digit_mask, prmt_sel) : (uint32_t)(RADIX - 1);
+        uint32_t peers = same_digit_lanes<RANK_BALLOT>(digit, minus_one);
+        if (!FULL) {
+            const uint32_t live_lanes = __ballot_sync(0xffffffffu, live);
+            peers = live ? (peers & live_lanes) : (1u << lane);  // padding lanes are nobody's peers
+        }
+        // upto = E * (lanes of my group up to and including me).  The highest lane of each group claims the group's slots
+        // (its upto is E * group size); every lane issues the atomic -- the others on a private dummy word -- so there is
+        // no branch.  My slot's address = (claimed base) + upto, thanks to the -E bias of the counters.
+        const uint32_t upto = E * (uint32_t)__popc(peers & le);
+        const bool leader = (peers & gt) == 0 && live;
+        uint32_t base = atom_add_shared(leader ? my_offset + 4u * digit : dummy, upto);
+        base = __shfl_sync(0xffffffffu, base, 31 - __clz(peers));
+        if (live) st_shared(base + upto, elem[i]);
+    }
+
+    // ---- 4. write-out ----
+    if (WO == WO_BULK) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the staged tile is read by the async proxy below
+        __syncthreads();
+        if (tid < RADIX && total) {
+            const uint32_t a = sbase & (uint32_t)(M - 1);
+            uint32_t head = (uint32_t)(M - a) & (uint32_t)(M - 1);  // elements before the first 16-byte boundary
+            if (head > total) head = total;
+            const uint32_t body = (total - head) & ~(uint32_t)(M - 1);
+            const uint32_t tail = total - head - body;
+            ElemT* g = out + exclusive;
+            const ElemT* sp = &s.staged[sbase];
+            if (body) bulk_copy_s2g(g + head, smem_addr(sp + head), body * E);
+#pragma unroll
+            for (int j = 0; j < M - 1; ++j)
+                if ((uint32_t)j < head) g[j] = sp[j];
+#pragma unroll
+            for (int j = 0; j < M - 1; ++j)
+                if ((uint32_t)j < tail) g[head + body + j] = sp[head + body + j];
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the copy's reads
+        }
+    } else {
+        if (tid < RADIX) {
+            if (ORDER == ORDER_LATE) exclusive = (uint64_t)digit_start[tid] + lookback3_resolve(lb, tile, pass, total, mates, tid);
+            s.run_ptr[tid] = (uint64_t)(uintptr_t)(out + exclusive) - (uint64_t)sbase * E;
+        }
+        __syncthreads();
+        const uint32_t run_ptr = smem_addr(&s.run_ptr[0]);
+        const uint64_t my_bytes = (uint64_t)tid * E;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const uint32_t j = (uint32_t)tid + (uint32_t)k * THREADS;
+            if (FULL || j < valid) {
+                const ElemT e = s.staged[j];
+                const uint32_t d = digit_of<BYTE_DIGIT>(Elem<ElemT>::key(e), shift, digit_mask, prmt_sel);
+                uint64_t base;
+                asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(run_ptr + 8u * d));
+                *reinterpret_cast<ElemT*>(base + my_bytes + (uint64_t)k * THREADS * E) = e;
+            }
+        }
+    }
+}
+
+template <typename ElemT, int THREADS, int IPT, int MIN_CTAS, int WO, int ORDER>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
+                 const unsigned long long* __restrict__ digit_start /*[RADIX]: exclusive scan of the pass's histogram*/, Lookback3 lb,
+                 uint32_t* ticket, uint32_t pass, uint32_t minus_one /* 0xffffffff, opaque to ptxas: see same_digit_lanes */) {
+    using Cfg = Onesweep2Config<ElemT, THREADS, IPT, WO>;
+    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(smem_raw);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) s.tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int i = tid; i < Cfg::WARPS * RADIX; i += THREADS) (&s.warp_offset[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s.tile;
+    const uint64_t tile_base = (uint64_t)tile * Cfg::TILE;
+    const uint32_t valid = (uint32_t)min((uint64_t)Cfg::TILE, n - tile_base);
+    const bool byte_digit = digit_mask == (uint32_t)(RADIX - 1);
+    const uint32_t prmt_sel = 0x4440u | (uint32_t)(shift >> 3);
+
+    if (valid == Cfg::TILE) {
+        if (byte_digit) onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, true, true>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one);
+        else            onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, true, false>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one);
+    } else {
+        onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, false, false>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one);
+    }
+}
+
+// In-place exclusive scan of each pass's 256-bin histogram: digit_start[p][d] = number of elements with a smaller digit.
+__global__ void __launch_bounds__(RADIX) digit_start_kernel(unsigned long long* __restrict__ ghist /*[passes][RADIX]*/) {
+    __shared__ uint64_t scratch[RADIX / 32];
+    unsigned long long* h = ghist + (size_t)blockIdx.x * RADIX;
+    const uint64_t x = h[threadIdx.x];
+    h[threadIdx.x] = block_exclusive_scan_256<uint64_t>(x, scratch, threadIdx.x);
+}

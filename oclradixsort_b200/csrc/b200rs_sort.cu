@@ -479,6 +479,8 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
     }
 }
 
+#include "b200rs_onesweep2.cuh"
+
 // ---- host side -------------------------------------------------------------------------------------
 
 // Compiled variants; index chosen by B200RS_KEYS_VARIANT / B200RS_PAIRS_VARIANT (development knob), default 0.
@@ -487,11 +489,14 @@ struct Variant {
     int threads, ipt;
     size_t smem;
     const char* name;
+    int gen;  // 1: onesweep_kernel (tagged per-digit look-back), 2: onesweep2_kernel (per-tile flags, bulk write-out)
 };
 #define B200RS_VARIANT(ElemT, THREADS, IPT, MODE, MIN_CTAS) \
-    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS}
+    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS, 1}
 #define B200RS_VARIANT_W(ElemT, THREADS, IPT, MODE, MIN_CTAS, W) \
-    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS, false, false, W>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS "w" #W}
+    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS, false, false, W>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS "w" #W, 1}
+#define B200RS_VARIANT2(ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER) \
+    Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":" #WO ":" #ORDER, 2}
 
 template <typename ElemT> struct Variants;
 template <> struct Variants<uint32_t> {
@@ -508,11 +513,20 @@ template <> struct Variants<uint32_t> {
             B200RS_VARIANT_W(uint32_t, 512, 24, RANK_BALLOT, 3, 16),  // 8
             B200RS_VARIANT_W(uint32_t, 512, 24, RANK_BALLOT, 3, 2),   // 9
             B200RS_VARIANT_W(uint32_t, 512, 24, RANK_BALLOT, 3, 1),   // 10
+            B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_ELEM, ORDER_LATE),   // 11
+            B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_ELEM, ORDER_EARLY),  // 12
+            B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_BULK, ORDER_EARLY),  // 13
+            B200RS_VARIANT2(uint32_t, 512, 20, 3, WO_ELEM, ORDER_LATE),   // 14
+            B200RS_VARIANT2(uint32_t, 384, 24, 4, WO_ELEM, ORDER_LATE),   // 15
+            B200RS_VARIANT2(uint32_t, 1024, 16, 1, WO_ELEM, ORDER_LATE),  // 16
+            B200RS_VARIANT2(uint32_t, 768, 24, 2, WO_ELEM, ORDER_LATE),   // 17
+            B200RS_VARIANT2(uint32_t, 768, 24, 2, WO_BULK, ORDER_EARLY),  // 18
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
     }
     static const char* env() { return "B200RS_KEYS_VARIANT"; }
+    static int default_index() { return 14; }
 };
 template <> struct Variants<uint2> {
     static const Variant* list(int* count) {
@@ -525,21 +539,32 @@ template <> struct Variants<uint2> {
             B200RS_VARIANT_W(uint2, 384, 16, RANK_BALLOT, 3, 8),   // 5
             B200RS_VARIANT_W(uint2, 384, 16, RANK_BALLOT, 3, 16),  // 6
             B200RS_VARIANT_W(uint2, 384, 16, RANK_BALLOT, 3, 2),   // 7
+            B200RS_VARIANT2(uint2, 384, 16, 3, WO_ELEM, ORDER_LATE),   // 8
+            B200RS_VARIANT2(uint2, 384, 16, 3, WO_ELEM, ORDER_EARLY),  // 9
+            B200RS_VARIANT2(uint2, 384, 16, 3, WO_BULK, ORDER_EARLY),  // 10
+            B200RS_VARIANT2(uint2, 512, 16, 2, WO_ELEM, ORDER_LATE),   // 11
+            B200RS_VARIANT2(uint2, 512, 16, 2, WO_BULK, ORDER_EARLY),  // 12
+            B200RS_VARIANT2(uint2, 512, 12, 3, WO_ELEM, ORDER_LATE),   // 13
+            B200RS_VARIANT2(uint2, 512, 12, 3, WO_BULK, ORDER_EARLY),  // 14
+            B200RS_VARIANT2(uint2, 768, 12, 2, WO_ELEM, ORDER_LATE),   // 15
+            B200RS_VARIANT2(uint2, 768, 12, 2, WO_BULK, ORDER_EARLY),  // 16
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
     }
     static const char* env() { return "B200RS_PAIRS_VARIANT"; }
+    static int default_index() { return 8; }
 };
 constexpr uint64_t MIN_TILE = 384 * 16;  // smallest tile among the variants: temp storage is sized for it
 
 template <typename ElemT>
-const Variant& pick_variant() {
+const Variant& pick_variant(bool need_gen1) {
     int count = 0;
     const Variant* v = Variants<ElemT>::list(&count);
     const char* e = getenv(Variants<ElemT>::env());
-    int idx = e ? atoi(e) : 0;
-    if (idx < 0 || idx >= count) idx = 0;
+    int idx = e ? atoi(e) : Variants<ElemT>::default_index();
+    if (idx < 0 || idx >= count) idx = Variants<ElemT>::default_index();
+    if (need_gen1 && v[idx].gen != 1) idx = 0;  // device-side element counts (multi-GPU sort) are a generation-1 feature
     return v[idx];
 }
 
@@ -560,7 +585,14 @@ int make_plan(uint64_t n, int sort_bits, SortPlan* p) {
     p->clear_off = off;
     p->hist_off = off;     off += b200rs_align_up(sizeof(unsigned long long) * MAX_PASSES * RADIX, 256);
     p->ticket_off = off;   off += 256;
-    p->lookback_off = off; off += b200rs_align_up((size_t)tiles * RADIX * sizeof(uint64_t), 256);
+    // generation 1: tiles x 256 tagged u64 words; generation 2: partial[tiles][256] u32 | group[tiles/LB_GROUP][256] u64
+    // (smaller); either way zeroed per sort
+    p->lookback_off = off;
+    {
+        const size_t gen1 = (size_t)tiles * RADIX * sizeof(uint64_t);
+        const size_t gen2 = b200rs_align_up((size_t)tiles * RADIX * sizeof(uint32_t), 256) + (size_t)((tiles + LB_GROUP - 1) / LB_GROUP) * RADIX * sizeof(uint64_t);
+        off += b200rs_align_up(gen1 > gen2 ? gen1 : gen2, 256);
+    }
     p->clear_bytes = off - p->clear_off;
     p->total_bytes = off ? off : 256;
     return B200RS_OK;
@@ -582,7 +614,7 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     if (n <= 1 || plan.passes == 0) return B200RS_OK;  // nothing to order
 
     b200rs_device_guard guard(dev);
-    const Variant& var = pick_variant<ElemT>();
+    const Variant& var = pick_variant<ElemT>(n_dev != nullptr);
     const uint64_t tile_elems = (uint64_t)var.threads * var.ipt;
     const uint32_t num_tiles = (uint32_t)((n + tile_elems - 1) / tile_elems);
     char* base = static_cast<char*>(temp);
@@ -591,8 +623,14 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     uint32_t* tickets = reinterpret_cast<uint32_t*>(base + plan.ticket_off);
     uint64_t* lookback = reinterpret_cast<uint64_t*>(base + plan.lookback_off);
     // zero the histograms, the tickets and the part of the look-back table this tiling uses
-    const size_t clear_bytes = (plan.lookback_off - plan.clear_off) + (size_t)num_tiles * RADIX * sizeof(uint64_t);
+    const size_t partial_bytes = b200rs_align_up((size_t)num_tiles * RADIX * sizeof(uint32_t), 256);
+    const size_t num_groups = ((size_t)num_tiles + LB_GROUP - 1) / LB_GROUP;
+    const size_t clear_bytes = (plan.lookback_off - plan.clear_off) +
+                               (var.gen == 2 ? partial_bytes + num_groups * RADIX * sizeof(uint64_t) : (size_t)num_tiles * RADIX * sizeof(uint64_t));
     B200RS_CUDA(cudaMemsetAsync(base + plan.clear_off, 0, clear_bytes, dev->stream));
+    Lookback3 lb2;
+    lb2.partial = reinterpret_cast<uint32_t*>(base + plan.lookback_off);
+    lb2.group = reinterpret_cast<uint64_t*>(base + plan.lookback_off + partial_bytes);
 
     const uint32_t key_mask = sort_bits == 32 ? 0xffffffffu : ((1u << sort_bits) - 1u);
     char label[48];
@@ -615,6 +653,10 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         }
     }
     B200RS_CUDA(cudaGetLastError());
+    if (var.gen == 2) {
+        b200rs_launch_scope scope(dev, "digit_start", (uint64_t)plan.passes * RADIX, (uint64_t)plan.passes * RADIX * 16);
+        digit_start_kernel<<<plan.passes, RADIX, 0, dev->stream>>>(ghist);
+    }
 
     B200RS_CUDA(cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
     ElemT* src = inout;
@@ -629,11 +671,13 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         uint64_t n_arg = n;
         const uint8_t* no_lut = nullptr;
         uint32_t minus_one = 0xffffffffu;
-        void* args[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lookback, &ticket, &tag_base, &no_lut, &n_dev, &minus_one};
+        uint32_t pass = (uint32_t)p;
+        void* args1[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lookback, &ticket, &tag_base, &no_lut, &n_dev, &minus_one};
+        void* args2[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lb2, &ticket, &pass, &minus_one};  // ghist_pass: pre-scanned (digit_start_kernel)
         snprintf(label, sizeof(label), "onesweep_%s_pass%d", what, p);
         {
             b200rs_launch_scope scope(dev, label, n, 2ull * n * sizeof(ElemT));
-            B200RS_CUDA(cudaLaunchKernel(var.kernel, dim3(num_tiles), dim3(var.threads), args, var.smem, dev->stream));
+            B200RS_CUDA(cudaLaunchKernel(var.kernel, dim3(num_tiles), dim3(var.threads), var.gen == 2 ? args2 : args1, var.smem, dev->stream));
         }
         ElemT* t = src; src = dst; dst = t;
     }
