@@ -495,8 +495,8 @@ struct Variant {
     Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS, 1}
 #define B200RS_VARIANT_W(ElemT, THREADS, IPT, MODE, MIN_CTAS, W) \
     Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS, false, false, W>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS "w" #W, 1}
-#define B200RS_VARIANT2(ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER) \
-    Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":" #WO ":" #ORDER, 2}
+#define B200RS_VARIANT2(ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER, LOAD) \
+    Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER, LOAD>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":" #WO ":" #ORDER ":" #LOAD, 2}
 
 template <typename ElemT> struct Variants;
 template <> struct Variants<uint32_t> {
@@ -513,14 +513,17 @@ template <> struct Variants<uint32_t> {
             B200RS_VARIANT_W(uint32_t, 512, 24, RANK_BALLOT, 3, 16),  // 8
             B200RS_VARIANT_W(uint32_t, 512, 24, RANK_BALLOT, 3, 2),   // 9
             B200RS_VARIANT_W(uint32_t, 512, 24, RANK_BALLOT, 3, 1),   // 10
-            B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_ELEM, ORDER_LATE),   // 11
-            B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_ELEM, ORDER_EARLY),  // 12
-            B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_BULK, ORDER_EARLY),  // 13
-            B200RS_VARIANT2(uint32_t, 512, 20, 3, WO_ELEM, ORDER_LATE),   // 14
-            B200RS_VARIANT2(uint32_t, 384, 24, 4, WO_ELEM, ORDER_LATE),   // 15
-            B200RS_VARIANT2(uint32_t, 1024, 16, 1, WO_ELEM, ORDER_LATE),  // 16
-            B200RS_VARIANT2(uint32_t, 768, 24, 2, WO_ELEM, ORDER_LATE),   // 17
-            B200RS_VARIANT2(uint32_t, 768, 24, 2, WO_BULK, ORDER_EARLY),  // 18
+            B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 11
+            B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 12
+            B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_BULK, ORDER_EARLY, LOAD_LDG),  // 13  measurement: bulk write-out
+            B200RS_VARIANT2(uint32_t, 512, 20, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 14  default
+            B200RS_VARIANT2(uint32_t, 512, 20, 3, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 15
+            B200RS_VARIANT2(uint32_t, 512, 16, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 16
+            B200RS_VARIANT2(uint32_t, 512, 16, 4, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 17
+            B200RS_VARIANT2(uint32_t, 384, 20, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 18
+            B200RS_VARIANT2(uint32_t, 384, 20, 4, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 19
+            B200RS_VARIANT2(uint32_t, 256, 24, 6, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 20
+            B200RS_VARIANT2(uint32_t, 640, 16, 3, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 21
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
@@ -539,15 +542,15 @@ template <> struct Variants<uint2> {
             B200RS_VARIANT_W(uint2, 384, 16, RANK_BALLOT, 3, 8),   // 5
             B200RS_VARIANT_W(uint2, 384, 16, RANK_BALLOT, 3, 16),  // 6
             B200RS_VARIANT_W(uint2, 384, 16, RANK_BALLOT, 3, 2),   // 7
-            B200RS_VARIANT2(uint2, 384, 16, 3, WO_ELEM, ORDER_LATE),   // 8
-            B200RS_VARIANT2(uint2, 384, 16, 3, WO_ELEM, ORDER_EARLY),  // 9
-            B200RS_VARIANT2(uint2, 384, 16, 3, WO_BULK, ORDER_EARLY),  // 10
-            B200RS_VARIANT2(uint2, 512, 16, 2, WO_ELEM, ORDER_LATE),   // 11
-            B200RS_VARIANT2(uint2, 512, 16, 2, WO_BULK, ORDER_EARLY),  // 12
-            B200RS_VARIANT2(uint2, 512, 12, 3, WO_ELEM, ORDER_LATE),   // 13
-            B200RS_VARIANT2(uint2, 512, 12, 3, WO_BULK, ORDER_EARLY),  // 14
-            B200RS_VARIANT2(uint2, 768, 12, 2, WO_ELEM, ORDER_LATE),   // 15
-            B200RS_VARIANT2(uint2, 768, 12, 2, WO_BULK, ORDER_EARLY),  // 16
+            B200RS_VARIANT2(uint2, 384, 16, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 8  default
+            B200RS_VARIANT2(uint2, 384, 16, 3, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 9
+            B200RS_VARIANT2(uint2, 384, 16, 3, WO_BULK, ORDER_EARLY, LOAD_LDG),  // 10  measurement: bulk write-out
+            B200RS_VARIANT2(uint2, 512, 12, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 11
+            B200RS_VARIANT2(uint2, 512, 12, 3, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 12
+            B200RS_VARIANT2(uint2, 256, 24, 4, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 13
+            B200RS_VARIANT2(uint2, 256, 24, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 14
+            B200RS_VARIANT2(uint2, 512, 16, 2, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 15
+            B200RS_VARIANT2(uint2, 384, 20, 2, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 16
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
