@@ -23,7 +23,8 @@
 
 enum WriteOut { WO_ELEM = 0, WO_BULK = 1 };
 enum LookbackOrder { ORDER_LATE = 0, ORDER_EARLY = 1 };
-enum TileLoad { LOAD_LDG = 0, LOAD_BULK = 1 };  // LOAD_BULK: one cp.async.bulk (TMA) brings the whole tile into shared memory
+enum TileLoad { LOAD_LDG = 0, LOAD_BULK = 1 };
+constexpr uint32_t PASS_IDENTITY = 1u;  // pass control word, see digit_start_kernel  // LOAD_BULK: one cp.async.bulk (TMA) brings the whole tile into shared memory
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
     uint32_t v;
@@ -49,6 +50,8 @@ struct Onesweep2Config {
         uint64_t scan_scratch[RADIX / 32];
         uint32_t dummy[32];                     // lanes that are not their group's leader aim their atomic here (bank = lane)
         uint32_t tile;
+        uint32_t ctl;
+        uint64_t n_eff;
     };
 };
 
@@ -185,7 +188,7 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
         const ElemT* __restrict__ src = in + tile_base + slice;
 #pragma unroll
         for (int i = 0; i < IPT; ++i)
-            if (FULL || slice + i * 32 < valid) elem[i] = src[i * 32];
+            if (FULL || slice + i * 32 < valid) elem[i] = __ldg(src + i * 32);  // read-only path: the input buffer is not written by this pass
     }
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
@@ -275,7 +278,6 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
         }
         __syncthreads();
         {
-            const uint32_t run_ptr = smem_addr(&s.run_ptr[0]);
             const uint64_t my_bytes = (uint64_t)tid * E;
 #pragma unroll
             for (int k = 0; k < IPT; ++k) {
@@ -283,9 +285,10 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
                 if (FULL || j < valid) {
                     const ElemT e = s.staged[j];
                     const uint32_t d = digit_of<BYTE_DIGIT>(Elem<ElemT>::key(e), shift, digit_mask, prmt_sel);
-                    uint64_t base;
-                    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(run_ptr + 8u * d));
-                    *reinterpret_cast<ElemT*>(base + my_bytes + (uint64_t)k * THREADS * E) = e;
+                    // A plain C++ store through a pointer rebuilt from an integer compiles to a GENERIC store (ST.E), and
+                    // that is deliberate: telling the compiler the address is global (__isGlobal / st.global) lets it hoist
+                    // all of the loop's shared-memory reads above the stores, which measured 4 % slower (keys and pairs).
+                    *reinterpret_cast<ElemT*>(s.run_ptr[d] + my_bytes + (uint64_t)k * THREADS * E) = e;
                 }
             }
         }
@@ -296,30 +299,56 @@ template <typename ElemT, int THREADS, int IPT, int MIN_CTAS, int WO, int ORDER,
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
                  const unsigned long long* __restrict__ digit_start /*[RADIX]: exclusive scan of the pass's histogram*/, Lookback3 lb,
-                 uint32_t* ticket, uint32_t pass, uint32_t minus_one /* 0xffffffff, opaque to ptxas: see same_digit_lanes */) {
+                 uint32_t* ticket, uint32_t pass, uint32_t minus_one /* 0xffffffff, opaque to ptxas: see same_digit_lanes */,
+                 const unsigned long long* __restrict__ n_dev, const uint32_t* __restrict__ pass_ctl) {
     using Cfg = Onesweep2Config<ElemT, THREADS, IPT, WO>;
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(smem_raw);
-
+    // Thread 0 fetches, concurrently, the tile ticket, the pass control word (digit_start_kernel: PASS_IDENTITY = every
+    // element has the same digit in this pass, so the pass moves nothing) and the device-side element count (multi-GPU
+    // sort): one L2 round trip for all three.
     const int tid = threadIdx.x;
     const bool in_aligned = ((uintptr_t)in & 15u) == 0;  // the bulk copy needs a 16-byte aligned source
     if (tid == 0) {
+        const uint32_t ctl = pass_ctl[pass];
+        const uint64_t n_eff = n_dev ? min(n, (uint64_t)*n_dev) : n;  // the grid was sized for the upper bound n
         const uint32_t t = atomicAdd(ticket, 1u);
         s.tile = t;
+        s.ctl = ctl;
+        s.n_eff = n_eff;
         if (LOAD == LOAD_BULK) {
             const uint32_t mbar = smem_addr(&s.mbar);
             mbar_init(mbar, 1);
             const uint64_t base = (uint64_t)t * Cfg::TILE;
-            if (in_aligned && base + Cfg::TILE <= n) bulk_copy_g2s(smem_addr(&s.staged[0]), in + base, Cfg::TILE * (uint32_t)sizeof(ElemT), mbar);
+            if (!(ctl & PASS_IDENTITY) && in_aligned && base + Cfg::TILE <= n_eff)
+                bulk_copy_g2s(smem_addr(&s.staged[0]), in + base, Cfg::TILE * (uint32_t)sizeof(ElemT), mbar);
         }
     }
 #pragma unroll
     for (int i = tid; i < Cfg::WARPS * RADIX; i += THREADS) (&s.warp_offset[0][0])[i] = 0;
     __syncthreads();
+    n = s.n_eff;
     const uint32_t tile = s.tile;
     const uint64_t tile_base = (uint64_t)tile * Cfg::TILE;
+    if (tile_base >= n) return;  // only when n came from n_dev: surplus CTAs (nobody looks back at them)
     const uint32_t valid = (uint32_t)min((uint64_t)Cfg::TILE, n - tile_base);
+    if (s.ctl & PASS_IDENTITY) {
+        // identity pass: the tile is copied straight across (the buffers keep ping-ponging on the host's schedule);
+        // no counting, ranking or look-back -- about half the time of a real pass for keys
+        const ElemT* __restrict__ src = in + tile_base;
+        ElemT* __restrict__ dst = out + tile_base;
+        if (valid == Cfg::TILE && ((((uintptr_t)in | (uintptr_t)out) & 15u) == 0)) {
+            constexpr int VECS = Cfg::TILE * (int)sizeof(ElemT) / 16;
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll 4
+            for (int v = tid; v < VECS; v += THREADS) d4[v] = __ldg(s4 + v);
+        } else {
+            for (uint32_t j = tid; j < valid; j += THREADS) dst[j] = src[j];
+        }
+        return;
+    }
     const bool byte_digit = digit_mask == (uint32_t)(RADIX - 1);
     const uint32_t prmt_sel = 0x4440u | (uint32_t)(shift >> 3);
 
@@ -331,10 +360,18 @@ onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t
     }
 }
 
-// In-place exclusive scan of each pass's 256-bin histogram: digit_start[p][d] = number of elements with a smaller digit.
-__global__ void __launch_bounds__(RADIX) digit_start_kernel(unsigned long long* __restrict__ ghist /*[passes][RADIX]*/) {
+// One CTA, after the histogram kernel.  For each pass: in-place exclusive scan of its 256-bin histogram
+// (digit_start[p][d] = number of elements with a smaller digit) and the pass control word: a pass in which one digit
+// holds every element moves nothing, so its kernel only copies (PASS_IDENTITY).
+__global__ void __launch_bounds__(RADIX) digit_start_kernel(unsigned long long* __restrict__ ghist /*[passes][RADIX]*/, int passes, uint64_t n,
+                                                            const unsigned long long* __restrict__ n_dev, uint32_t* __restrict__ ctl) {
     __shared__ uint64_t scratch[RADIX / 32];
-    unsigned long long* h = ghist + (size_t)blockIdx.x * RADIX;
-    const uint64_t x = h[threadIdx.x];
-    h[threadIdx.x] = block_exclusive_scan_256<uint64_t>(x, scratch, threadIdx.x);
+    if (n_dev) n = min(n, (uint64_t)*n_dev);
+    for (int p = 0; p < passes; ++p) {
+        unsigned long long* h = ghist + (size_t)p * RADIX;
+        const uint64_t x = h[threadIdx.x];
+        const int degenerate = __syncthreads_or(x == n);
+        h[threadIdx.x] = block_exclusive_scan_256<uint64_t>(x, scratch, threadIdx.x);
+        if (threadIdx.x == 0) ctl[p] = degenerate ? PASS_IDENTITY : 0u;
+    }
 }

@@ -561,13 +561,12 @@ template <> struct Variants<uint2> {
 constexpr uint64_t MIN_TILE = 384 * 16;  // smallest tile among the variants: temp storage is sized for it
 
 template <typename ElemT>
-const Variant& pick_variant(bool need_gen1) {
+const Variant& pick_variant() {
     int count = 0;
     const Variant* v = Variants<ElemT>::list(&count);
     const char* e = getenv(Variants<ElemT>::env());
     int idx = e ? atoi(e) : Variants<ElemT>::default_index();
     if (idx < 0 || idx >= count) idx = Variants<ElemT>::default_index();
-    if (need_gen1 && v[idx].gen != 1) idx = 0;  // device-side element counts (multi-GPU sort) are a generation-1 feature
     return v[idx];
 }
 
@@ -617,7 +616,7 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     if (n <= 1 || plan.passes == 0) return B200RS_OK;  // nothing to order
 
     b200rs_device_guard guard(dev);
-    const Variant& var = pick_variant<ElemT>(n_dev != nullptr);
+    const Variant& var = pick_variant<ElemT>();
     const uint64_t tile_elems = (uint64_t)var.threads * var.ipt;
     const uint32_t num_tiles = (uint32_t)((n + tile_elems - 1) / tile_elems);
     char* base = static_cast<char*>(temp);
@@ -656,9 +655,10 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         }
     }
     B200RS_CUDA(cudaGetLastError());
+    uint32_t* pass_ctl = tickets + 32;  // [passes], inside the zeroed ticket block
     if (var.gen == 2) {
         b200rs_launch_scope scope(dev, "digit_start", (uint64_t)plan.passes * RADIX, (uint64_t)plan.passes * RADIX * 16);
-        digit_start_kernel<<<plan.passes, RADIX, 0, dev->stream>>>(ghist);
+        digit_start_kernel<<<1, RADIX, 0, dev->stream>>>(ghist, plan.passes, n, n_dev, pass_ctl);
     }
 
     B200RS_CUDA(cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
@@ -676,7 +676,7 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         uint32_t minus_one = 0xffffffffu;
         uint32_t pass = (uint32_t)p;
         void* args1[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lookback, &ticket, &tag_base, &no_lut, &n_dev, &minus_one};
-        void* args2[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lb2, &ticket, &pass, &minus_one};  // ghist_pass: pre-scanned (digit_start_kernel)
+        void* args2[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lb2, &ticket, &pass, &minus_one, &n_dev, &pass_ctl};  // ghist_pass: pre-scanned
         snprintf(label, sizeof(label), "onesweep_%s_pass%d", what, p);
         {
             b200rs_launch_scope scope(dev, label, n, 2ull * n * sizeof(ElemT));

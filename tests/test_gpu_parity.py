@@ -112,6 +112,38 @@ def test_sort_pairs_stability(ctx, kind):
         assert np.array_equal(got, po.sort_pairs(kv)), (kind, n)
 
 
+# The scatter pass groups tiles by 8 for its two-level look-back (csrc/b200rs_onesweep2.cuh, LB_GROUP); tiles are
+# 10240 keys / 6144 pairs.  Sizes around whole groups, one tile more, one element less, and several groups deep.
+GROUP_EDGE_TILES = [7, 8, 9, 16, 17, 41]
+
+
+@pytest.mark.parametrize("tiles", GROUP_EDGE_TILES)
+def test_sort_lookback_group_boundaries(ctx, tiles):
+    ob = ctx[0]
+    for n in (tiles * 10240 - 1, tiles * 10240, tiles * 10240 + 1):
+        k = _keys("and3", n)  # low entropy: long equal-key runs cross tile and group edges
+        assert np.array_equal(_sort_keys(ctx, k), po.sort_u32(k)), n
+    for n in (tiles * 6144 - 1, tiles * 6144, tiles * 6144 + 1):
+        kv = np.empty(n, dtype=ob.PAIR_DTYPE)
+        kv["key"], kv["value"] = _keys("few", n), np.arange(n, dtype=np.uint32)
+        assert np.array_equal(_sort_pairs(ctx, kv), po.sort_pairs(kv)), n
+
+
+@pytest.mark.parametrize("mask", [0x000000FF, 0x0000FF00, 0x00FF0000, 0xFF000000, 0x00FFFF00, 0xFF0000FF, 0x00FF00FF, 0xFFFF0000, 0x0])
+def test_sort_skipped_passes(ctx, mask):
+    """A pass whose digit is the same for every element moves nothing: the device detects it (digit_start_kernel) and
+    that pass's kernel only copies its tiles; 0, 1, 2, 3 or 4 real passes then run."""
+    ob = ctx[0]
+    n = 150001
+    k = (_keys("uniform", n) & np.uint32(mask)) | np.uint32(0x5A5A5A5A & ~mask)
+    assert np.array_equal(_sort_keys(ctx, k), po.sort_u32(k)), hex(mask)
+    for bits in (16, 24):
+        assert np.array_equal(_sort_keys(ctx, k, bits), po.sort_u32(k, bits)), (hex(mask), bits)
+    kv = np.empty(n, dtype=ob.PAIR_DTYPE)
+    kv["key"], kv["value"] = k, np.arange(n, dtype=np.uint32)[::-1]
+    assert np.array_equal(_sort_pairs(ctx, kv), po.sort_pairs(kv)), hex(mask)
+
+
 @pytest.mark.parametrize("bits", [4, 12, 16, 24])
 def test_sort_pairs_partial_bits(ctx, bits):
     ob = ctx[0]
