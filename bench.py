@@ -302,13 +302,13 @@ def main() -> None:
             hist = [e for e in prof if e["kernel"].startswith("digit_histogram")]
             avg_ms = sum(e["ms"] for e in scatter) / len(scatter)
             achieved = scatter[0]["bytes"] / (avg_ms * 1e-3) / 1e9
-            traffic = None
+            traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
             try:
                 with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                    traffic = json.load(f).get("onesweep_pairs_dram_bytes_per_launch_2^28")
+                    traffic = json.load(f).get(f"onesweep_pairs_dram_bytes_per_launch_2^{args.log2_pairs_per_gpu}")
             except Exception:
                 pass
-            roofline = {"bound": "hbm", "kernel": "onesweep_kernel<uint2> (one scatter pass, 4 per sort)", "achieved": achieved, "peak": peak,
+            roofline = {"bound": "hbm", "kernel": "onesweep2_kernel<uint2, 384 threads x 16 pairs> (one scatter pass, 4 per sort)", "achieved": achieved, "peak": peak,
                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": scatter[0]["bytes"],
                         "whole_sort": {"algorithmic_bytes": 72 * n, "achieved": 72 * n / (ms_per_step * 1e-3) / 1e9,
