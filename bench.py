@@ -238,6 +238,11 @@ def main() -> None:
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        if dist is not None:
+            # ranks leave the host-side barrier milliseconds apart; a stream-ordered all-reduce lines the GPUs up so that
+            # the first timed step does not include the other ranks' launch skew (the host barrier + synchronize stay)
+            align = torch.zeros(1, device="cuda")
+            dist.all_reduce(align)
         e0.record(stream)
         for i in range(args.warmup, nbuf):
             step(i)

@@ -516,7 +516,7 @@ template <> struct Variants<uint32_t> {
             B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 11
             B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 12
             B200RS_VARIANT2(uint32_t, 512, 24, 3, WO_BULK, ORDER_EARLY, LOAD_LDG),  // 13  measurement: bulk write-out
-            B200RS_VARIANT2(uint32_t, 512, 20, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 14  default
+            B200RS_VARIANT2(uint32_t, 512, 20, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 14
             B200RS_VARIANT2(uint32_t, 512, 20, 3, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 15
             B200RS_VARIANT2(uint32_t, 512, 16, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 16
             B200RS_VARIANT2(uint32_t, 512, 16, 4, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 17
@@ -524,12 +524,24 @@ template <> struct Variants<uint32_t> {
             B200RS_VARIANT2(uint32_t, 384, 20, 4, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 19
             B200RS_VARIANT2(uint32_t, 256, 24, 6, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 20
             B200RS_VARIANT2(uint32_t, 640, 16, 3, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 21
+            B200RS_VARIANT2(uint32_t, 256, 24, 5, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 22  51 registers
+            B200RS_VARIANT2(uint32_t, 384, 24, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 23  56 registers
+            B200RS_VARIANT2(uint32_t, 640, 16, 2, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 24  51 registers
+            B200RS_VARIANT2(uint32_t, 256, 32, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 25  default (48 registers, no spills)
+            B200RS_VARIANT2(uint32_t, 320, 24, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 26  51 registers
+            B200RS_VARIANT2(uint32_t, 512, 20, 2, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 27  64 registers, 2 CTAs
+            B200RS_VARIANT2(uint32_t, 256, 32, 5, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 28
+            B200RS_VARIANT2(uint32_t, 256, 28, 5, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 29
+            B200RS_VARIANT2(uint32_t, 256, 40, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 30
+            B200RS_VARIANT2(uint32_t, 256, 48, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 31
+            B200RS_VARIANT2(uint32_t, 256, 36, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 32
+            B200RS_VARIANT2(uint32_t, 256, 32, 4, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 33
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
     }
     static const char* env() { return "B200RS_KEYS_VARIANT"; }
-    static int default_index() { return 14; }
+    static int default_index() { return 25; }  // 256 threads x 32 keys, 4 CTAs/SM
 };
 template <> struct Variants<uint2> {
     static const Variant* list(int* count) {
@@ -551,6 +563,12 @@ template <> struct Variants<uint2> {
             B200RS_VARIANT2(uint2, 256, 24, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 14
             B200RS_VARIANT2(uint2, 512, 16, 2, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 15
             B200RS_VARIANT2(uint2, 384, 20, 2, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 16
+            B200RS_VARIANT2(uint2, 256, 24, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 17
+            B200RS_VARIANT2(uint2, 256, 28, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 18
+            B200RS_VARIANT2(uint2, 256, 32, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 19
+            B200RS_VARIANT2(uint2, 256, 24, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 20 (= 14)
+            B200RS_VARIANT2(uint2, 320, 20, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 21
+            B200RS_VARIANT2(uint2, 288, 24, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 22
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;

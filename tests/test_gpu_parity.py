@@ -113,14 +113,14 @@ def test_sort_pairs_stability(ctx, kind):
 
 
 # The scatter pass groups tiles by 8 for its two-level look-back (csrc/b200rs_onesweep2.cuh, LB_GROUP); tiles are
-# 10240 keys / 6144 pairs.  Sizes around whole groups, one tile more, one element less, and several groups deep.
+# 8192 keys / 6144 pairs.  Sizes around whole groups, one tile more, one element less, and several groups deep.
 GROUP_EDGE_TILES = [7, 8, 9, 16, 17, 41]
 
 
 @pytest.mark.parametrize("tiles", GROUP_EDGE_TILES)
 def test_sort_lookback_group_boundaries(ctx, tiles):
     ob = ctx[0]
-    for n in (tiles * 10240 - 1, tiles * 10240, tiles * 10240 + 1):
+    for n in (tiles * 8192 - 1, tiles * 8192, tiles * 8192 + 1, tiles * 10240 + 1):
         k = _keys("and3", n)  # low entropy: long equal-key runs cross tile and group edges
         assert np.array_equal(_sort_keys(ctx, k), po.sort_u32(k)), n
     for n in (tiles * 6144 - 1, tiles * 6144, tiles * 6144 + 1):
