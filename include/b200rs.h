@@ -156,6 +156,12 @@ int b200rs_sort_keys_u32_host(b200rs_device* dev, uint32_t* host_inout, uint64_t
 int b200rs_sort_pairs_u32_host(b200rs_device* dev, b200rs_pair* host_inout, uint64_t n, int sort_bits);
 int b200rs_exclusive_scan_u32_host(b200rs_device* dev, uint32_t* host_dst, const uint32_t* host_src, uint64_t n,
                                    uint32_t* host_total_out);
+/* Batch forms: `count` independent host arrays of n elements each, every one sorted in place -- the size sweep of
+ * UnitTest/main.cpp:105-171 run as one call.  Pipelined over three streams and two device buffers: array i+1 is copied
+ * in and array i-1 copied out while array i is sorted, so both directions of the host link are busy at once.  Use pinned
+ * host memory (b200rs_host_alloc); with pageable memory the copies serialise. */
+int b200rs_sort_keys_u32_host_batch(b200rs_device* dev, uint32_t* const* host_inout, int count, uint64_t n, int sort_bits);
+int b200rs_sort_pairs_u32_host_batch(b200rs_device* dev, b200rs_pair* const* host_inout, int count, uint64_t n, int sort_bits);
 int b200rs_device_release_scratch(b200rs_device* dev);
 
 /* ---- per-launch timing: replaces Device::toggleProfiling, Adl/Adl.h:142 + AdlKernelUtilsCL.inl:654-677 */

@@ -57,6 +57,8 @@ SIGNATURES = {
     "b200rs_ipc_release": (_int, [c_dev, _vp]),
     "b200rs_sort_keys_u32_host": (_int, [c_dev, _vp, _u64, _int]),
     "b200rs_sort_pairs_u32_host": (_int, [c_dev, _vp, _u64, _int]),
+    "b200rs_sort_keys_u32_host_batch": (_int, [c_dev, _vp, _int, _u64, _int]),
+    "b200rs_sort_pairs_u32_host_batch": (_int, [c_dev, _vp, _int, _u64, _int]),
     "b200rs_exclusive_scan_u32_host": (_int, [c_dev, _vp, _vp, _u64, _P(ctypes.c_uint32)]),
     "b200rs_device_release_scratch": (_int, [c_dev]),
     "b200rs_profile_enable": (_int, [c_dev, _int]),

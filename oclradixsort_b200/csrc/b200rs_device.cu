@@ -94,6 +94,14 @@ int b200rs_device_destroy(b200rs_device* dev) {
         cudaEventDestroy(s.stop);
     }
     if (dev->pinned_word) cudaFreeHost(dev->pinned_word);
+    for (int i = 0; i < 2; ++i) {
+        if (dev->ev_in[i]) cudaEventDestroy(dev->ev_in[i]);
+        if (dev->ev_sorted[i]) cudaEventDestroy(dev->ev_sorted[i]);
+        if (dev->ev_out[i]) cudaEventDestroy(dev->ev_out[i]);
+    }
+    if (dev->ev_start) cudaEventDestroy(dev->ev_start);
+    if (dev->copy_in) cudaStreamDestroy(dev->copy_in);
+    if (dev->copy_out) cudaStreamDestroy(dev->copy_out);
     if (dev->owns_stream && dev->stream) cudaStreamDestroy(dev->stream);
     delete dev;
     return rc;

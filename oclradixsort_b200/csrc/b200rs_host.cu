@@ -25,7 +25,69 @@ int sort_host(b200rs_device* dev, void* host_inout, uint64_t n, size_t elem_byte
     return B200RS_OK;
 }
 
+// Batch form: `count` independent host arrays of n elements each, every one sorted in place.  Three streams: the
+// host -> device copy of array i+1 and the device -> host copy of array i-1 run while array i is being sorted (two
+// device buffers), so both directions of the host link are busy at once; the sorts themselves stay on the handle's
+// stream and share one temp block.
+template <typename SortFn>
+int sort_host_batch(b200rs_device* dev, void* const* host_inout, int count, uint64_t n, size_t elem_bytes, int sort_bits, SortFn sort_fn) {
+    if (!dev || count < 0 || (count && !host_inout)) return B200RS_ERR_INVALID_ARGUMENT;
+    if (sort_bits < 0 || sort_bits > 32) return B200RS_ERR_INVALID_ARGUMENT;
+    if (n == 0 || count == 0) return B200RS_OK;
+    for (int i = 0; i < count; ++i)
+        if (!host_inout[i]) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    if (!dev->copy_in) {
+        B200RS_CUDA(cudaStreamCreateWithFlags(&dev->copy_in, cudaStreamNonBlocking));
+        B200RS_CUDA(cudaStreamCreateWithFlags(&dev->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_in[i], cudaEventDisableTiming));
+            B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_sorted[i], cudaEventDisableTiming));
+            B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_out[i], cudaEventDisableTiming));
+        }
+        B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_start, cudaEventDisableTiming));
+    }
+    size_t temp_bytes = 0;
+    B200RS_TRY(sort_fn(nullptr, nullptr, &temp_bytes));
+    const size_t data_bytes = (size_t)n * elem_bytes;
+    B200RS_TRY(b200rs_reserve(dev, &dev->scratch_data, &dev->scratch_data_bytes, data_bytes));
+    if (count > 1) B200RS_TRY(b200rs_reserve(dev, &dev->scratch_data2, &dev->scratch_data2_bytes, data_bytes));
+    B200RS_TRY(b200rs_reserve(dev, &dev->scratch_temp, &dev->scratch_temp_bytes, temp_bytes));
+    void* buf[2] = {dev->scratch_data, dev->scratch_data2};
+    // whatever the handle's stream was doing with the scratch buffers comes first
+    B200RS_CUDA(cudaEventRecord(dev->ev_start, dev->stream));
+    B200RS_CUDA(cudaStreamWaitEvent(dev->copy_in, dev->ev_start, 0));
+    for (int i = 0; i < count; ++i) {
+        const int b = i & 1;
+        if (i >= 2) B200RS_CUDA(cudaStreamWaitEvent(dev->copy_in, dev->ev_out[b], 0));  // array i-2 has left buffer b
+        B200RS_CUDA(cudaMemcpyAsync(buf[b], host_inout[i], data_bytes, cudaMemcpyHostToDevice, dev->copy_in));
+        B200RS_CUDA(cudaEventRecord(dev->ev_in[b], dev->copy_in));
+        B200RS_CUDA(cudaStreamWaitEvent(dev->stream, dev->ev_in[b], 0));
+        size_t have = dev->scratch_temp_bytes;
+        B200RS_TRY(sort_fn(buf[b], dev->scratch_temp, &have));
+        B200RS_CUDA(cudaEventRecord(dev->ev_sorted[b], dev->stream));
+        B200RS_CUDA(cudaStreamWaitEvent(dev->copy_out, dev->ev_sorted[b], 0));
+        B200RS_CUDA(cudaMemcpyAsync(host_inout[i], buf[b], data_bytes, cudaMemcpyDeviceToHost, dev->copy_out));
+        B200RS_CUDA(cudaEventRecord(dev->ev_out[b], dev->copy_out));
+    }
+    B200RS_CUDA(cudaStreamSynchronize(dev->copy_out));
+    B200RS_CUDA(cudaStreamSynchronize(dev->stream));
+    return B200RS_OK;
+}
+
 }  // namespace
+
+extern "C" int b200rs_sort_keys_u32_host_batch(b200rs_device* dev, uint32_t* const* host_inout, int count, uint64_t n, int sort_bits) {
+    return sort_host_batch(dev, reinterpret_cast<void* const*>(host_inout), count, n, sizeof(uint32_t), sort_bits, [&](void* data, void* temp, size_t* temp_bytes) {
+        return b200rs_sort_keys_u32(dev, static_cast<uint32_t*>(data), n, sort_bits, temp, temp_bytes);
+    });
+}
+
+extern "C" int b200rs_sort_pairs_u32_host_batch(b200rs_device* dev, b200rs_pair* const* host_inout, int count, uint64_t n, int sort_bits) {
+    return sort_host_batch(dev, reinterpret_cast<void* const*>(host_inout), count, n, sizeof(b200rs_pair), sort_bits, [&](void* data, void* temp, size_t* temp_bytes) {
+        return b200rs_sort_pairs_u32(dev, static_cast<b200rs_pair*>(data), n, sort_bits, temp, temp_bytes);
+    });
+}
 
 extern "C" int b200rs_sort_keys_u32_host(b200rs_device* dev, uint32_t* host_inout, uint64_t n, int sort_bits) {
     return sort_host(dev, host_inout, n, sizeof(uint32_t), sort_bits, [&](void* data, void* temp, size_t* temp_bytes) {

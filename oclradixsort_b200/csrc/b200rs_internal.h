@@ -35,6 +35,10 @@ struct b200rs_device {
     size_t scratch_temp_bytes = 0;
     uint32_t* pinned_word = nullptr;  // 1-word pinned mailbox (scan total)
 
+    // copy streams + events of the pipelined host-batch entry points (created on first use)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_sorted[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_start = nullptr;
+
     bool profiling = false;
     std::vector<b200rs_profile_span> spans;
 };

@@ -257,6 +257,36 @@ def test_host_buffer_entry_points(ctx):
     check(lib().b200rs_device_release_scratch(d.handle), "release_scratch")
 
 
+def test_host_batch_entry_points(ctx):
+    """b200rs_sort_*_host_batch: several host arrays sorted in place by one pipelined call (1, 2, 3 and 5 arrays: the
+    double buffering wraps around), pageable and pinned memory, against the oracle."""
+    import torch
+    ob, d, p = ctx
+    from oclradixsort_b200._lib import check, lib
+    n = 70001
+    for count in (1, 2, 3, 5):
+        arrays = [_keys("and3" if i % 2 else "uniform", n, seed=10 + i) for i in range(count)]
+        got = [a.copy() for a in arrays]
+        ptrs = (ctypes.c_void_p * count)(*[g.ctypes.data for g in got])
+        check(lib().b200rs_sort_keys_u32_host_batch(d.handle, ptrs, count, n, 32), "sort_keys_host_batch")
+        for a, g in zip(arrays, got):
+            assert np.array_equal(g, po.sort_u32(a)), count
+    count = 4
+    pinned = [torch.empty((n, 2), dtype=torch.int32).pin_memory() for _ in range(count)]
+    want = []
+    for i, t in enumerate(pinned):
+        kv = np.empty(n, dtype=ob.PAIR_DTYPE)
+        kv["key"], kv["value"] = _keys("few" if i % 2 else "uniform", n, seed=20 + i), np.arange(n, dtype=np.uint32)[::-1]
+        t.numpy().view(np.uint32)[:] = kv.view(np.uint32).reshape(n, 2)
+        want.append(po.sort_pairs(kv))
+    ptrs = (ctypes.c_void_p * count)(*[t.data_ptr() for t in pinned])
+    check(lib().b200rs_sort_pairs_u32_host_batch(d.handle, ptrs, count, n, 32), "sort_pairs_host_batch")
+    for t, w in zip(pinned, want):
+        assert np.array_equal(t.numpy().view(np.uint32).reshape(n, 2), w.view(np.uint32).reshape(n, 2))
+    assert lib().b200rs_sort_pairs_u32_host_batch(d.handle, None, 2, n, 32) != 0  # null array list is an error
+    check(lib().b200rs_device_release_scratch(d.handle), "release_scratch")
+
+
 def test_empty_inputs_and_errors(ctx):
     ob, d, p = ctx
     from oclradixsort_b200._lib import lib
