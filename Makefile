@@ -9,7 +9,7 @@ REF    ?= /root/reference
 ARCH   := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v -Iinclude
 CSRC   := oclradixsort_b200/csrc
-SRCS   := $(CSRC)/b200rs_device.cu $(CSRC)/b200rs_scan.cu $(CSRC)/b200rs_sort.cu $(CSRC)/b200rs_host.cu
+SRCS   := $(CSRC)/b200rs_device.cu $(CSRC)/b200rs_scan.cu $(CSRC)/b200rs_sort.cu $(CSRC)/b200rs_host.cu $(CSRC)/b200rs_prims.cu
 OBJS   := $(SRCS:.cu=.o)
 LIB    := oclradixsort_b200/libb200rs.so
 
@@ -52,3 +52,20 @@ unittest: $(LIB)
 # Same program, but with the CPU check provided by the repo's own oracle (buildable without $(REF) sources
 # except main.cpp/gtest, kept for symmetry; not used on the GPU box).
 .PHONY: unittest
+
+# External comparison only (north_star): CUB DeviceRadixSort / DeviceScan timed on the same sizes.  A stand-alone
+# binary under tools/_build/ (git-ignored, travels to the GPU box); the product never links or calls it.
+cub_compare: tools/_build/cub_compare
+tools/_build/cub_compare: tools/cub_compare.cu
+	mkdir -p tools/_build
+	$(NVCC) $(ARCH) -O3 -std=c++17 -o $@ $<
+.PHONY: cub_compare
+
+# C++ caller of the drop-in headers for the section-8f rows (copy/fill, Stopwatch, profile CSV); needs no reference
+# sources.  tools/_build/ is git-ignored and travels to the GPU box; run by tests/test_gpu_prims.py.
+prims_test: tools/_build/prims_dropin
+tools/_build/prims_dropin: tests/cpp/prims_dropin.cpp $(CSRC)/Pprims.cpp $(LIB) $(wildcard include/Adl/*.h include/Tahoe/*/*.h include/Tahoe/*/*/*.h)
+	mkdir -p tools/_build
+	$(CXX) -std=c++11 -O2 -Wall -DNDEBUG -Iinclude tests/cpp/prims_dropin.cpp $(CSRC)/Pprims.cpp \
+	    -Loclradixsort_b200 -lb200rs -Wl,-rpath,'$$ORIGIN/../../oclradixsort_b200' -o $@
+.PHONY: prims_test

@@ -131,6 +131,30 @@ struct Device {
         m_enableProfiling = enable;
         if (m_handle) b200rs_profile_enable(m_handle, enable ? 1 : 0);
     }
+    // Appends the per-launch log recorded since the last call to `path` (default "ProfileB200.<device name>.csv"),
+    // one line per launch: "kernel","ms","elements","bytes","GB/s" -- the reference appends
+    // "kernel","ms","global size x","y","y" to ProfileCL.<device>.<driver>.csv per launch (AdlKernelUtilsCL.inl:663-676).
+    // Waits for the stream.  Returns the number of launches written.
+    int writeProfileCsv(const char* path = 0) {
+        if (!m_handle) return 0;
+        char name[128], file[256];
+        getDeviceName(name);
+        for (char* c = name; *c; ++c) if (*c == ' ' || *c == '/') *c = '_';
+        snprintf(file, sizeof(file), "ProfileB200.%s.csv", name);
+        FILE* f = fopen(path ? path : file, "a");
+        if (!f) return 0;
+        int total = 0, got = 0;
+        b200rs_profile_entry e[64];
+        do {
+            if (!adlCheck(b200rs_profile_read(m_handle, e, 64, &got), "b200rs_profile_read")) break;
+            for (int i = 0; i < got; ++i)
+                fprintf(f, "\"%s\",\"%g\",\"%llu\",\"%llu\",\"%g\"\n", e[i].kernel, e[i].ms, (unsigned long long)e[i].elements,
+                        (unsigned long long)e[i].bytes, e[i].ms > 0.f ? (double)e[i].bytes / e[i].ms * 1e-6 : 0.0);
+            total += got;
+        } while (got == 64);
+        fclose(f);
+        return total;
+    }
     void setBinaryFileVersion(unsigned int ver) { m_binaryFileVersion = ver; }
     unsigned int getBinaryFileVersion() const { return m_binaryFileVersion; }
     DeviceType getType() const { return m_type; }
@@ -468,5 +492,7 @@ void Buffer<T>::setSize(u64 size) {
 }
 
 }  // namespace adl
+
+#include <Adl/AdlStopwatch.h>
 
 #endif  // ADL_H

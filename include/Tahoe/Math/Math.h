@@ -37,6 +37,16 @@ struct int2 {
     };
 };
 
+// 16-byte POD {x, y, z, w}: the element type of Pprims::copy / Pprims::fill on float4 data (reference:
+// Math.h:95-111; the renderer algebra on it -- operators, dot3, cross3 ... -- is not on the path and not provided)
+struct __attribute__((aligned(16))) float4 {
+    union {
+        struct { float x, y, z, w; };
+        float s[4];
+    };
+};
+inline float4 make_float4(float x, float y, float z, float w = 0.f) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+
 struct int4 {
     union {
         struct { int x, y, z, w; };

@@ -40,6 +40,21 @@ public:
     // any n >= 0
     void radixSort(const adl::Device* device, const adl::Buffer<u32>& inout, int n, int sortBits = 32);
 
+    // Element-wise primitives: dst[i] = src[i] / dst[i] = src for i < n.  The reference declares them on uArray
+    // (Pprims.cpp:31-121; commented out there, the OpenCL kernels CopyIntKernel ... FillF4Kernel are still
+    // shipped, PprimsKernels.cl:9-48); the Buffer overloads are what those forward to.  Asynchronous.
+    void copy(const adl::Device* device, uArray<int>& dst, const uArray<int>& src, int n);
+    void copy(const adl::Device* device, uArray<float4>& dst, const uArray<float4>& src, int n);
+    void fill(const adl::Device* device, uArray<int>& dst, int src, int n);
+    void fill(const adl::Device* device, uArray<u32>& dst, u32 src, int n);
+    void fill(const adl::Device* device, uArray<float4>& dst, const float4& src, int n);
+    void copy(const adl::Device* device, adl::Buffer<int>& dst, const adl::Buffer<int>& src, int n);
+    void copy(const adl::Device* device, adl::Buffer<u32>& dst, const adl::Buffer<u32>& src, int n);
+    void copy(const adl::Device* device, adl::Buffer<float4>& dst, const adl::Buffer<float4>& src, int n);
+    void fill(const adl::Device* device, adl::Buffer<int>& dst, int src, int n);
+    void fill(const adl::Device* device, adl::Buffer<u32>& dst, u32 src, int n);
+    void fill(const adl::Device* device, adl::Buffer<float4>& dst, const float4& src, int n);
+
 private:
     void* reserveTemp(const adl::Device* device, size_t bytes);
     void releaseTemp();

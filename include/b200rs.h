@@ -109,6 +109,18 @@ int b200rs_exclusive_scan_u32(b200rs_device* dev, uint32_t* dst, const uint32_t*
                               void* temp, size_t* temp_bytes);
 
 /*
+ * Element-wise primitives of Tahoe/ParallelPrimitives: Pprims::copy / Pprims::fill,
+ * Pprims.cpp:31-121 (dormant in the reference: commented out on the host, kernels still shipped as
+ * CopyIntKernel / CopyF4Kernel / FillIntKernel / FillU32Kernel / FillF4Kernel, PprimsKernels.cl:9-48).
+ * dst[i] = src[i] / dst[i] = value for i in [0, n).  u32 forms: 4-byte aligned pointers, any n; u128 forms
+ * (float4 elements): 16-byte aligned pointers.  copy: dst and src must not partially overlap.
+ */
+int b200rs_copy_u32(b200rs_device* dev, uint32_t* dst, const uint32_t* src, uint64_t n);
+int b200rs_copy_u128(b200rs_device* dev, void* dst, const void* src, uint64_t n);
+int b200rs_fill_u32(b200rs_device* dev, uint32_t* dst, uint32_t value, uint64_t n);
+int b200rs_fill_u128(b200rs_device* dev, void* dst, const uint32_t value[4], uint64_t n);
+
+/*
  * Building blocks of the multi-GPU partitioned sort (new capability; the reference is single-device, SURVEY.md
  * section 8e).  Histogram of one key digit, and a STABLE partition of pairs by a 256-entry digit -> part table:
  * `out` receives part 0, then part 1, ... each in input order; part_counts[p] (device, 256 x u64, zero for unused
@@ -175,10 +187,19 @@ typedef struct b200rs_profile_entry {
 
 /* While enabled, every kernel the library launches is bracketed by CUDA events. */
 int b200rs_profile_enable(b200rs_device* dev, int enable);
-/* Synchronises the stream, writes up to `capacity` entries recorded since the last read, clears the log. */
+/* Synchronises the stream and moves up to `capacity` of the oldest recorded entries to `out`; *count = how many
+ * (== capacity means more may be queued: call again).  capacity 0 just synchronises. */
 int b200rs_profile_read(b200rs_device* dev, b200rs_profile_entry* out, int capacity, int* count);
 /* Number of kernels launched through this handle since creation (bench.py's gpu_launches). */
 int b200rs_device_launch_count(const b200rs_device* dev, uint64_t* launches);
+
+/* ---- device-side interval timing: what adl::Stopwatch measures with (Adl/AdlStopwatch.h:27-83; the reference's
+ * CL stopwatch is a host clock, Adl/AdlStopwatch.inl:16-19 -- asynchronous launches need events on the stream) ---- */
+int b200rs_event_create(b200rs_device* dev, void** event_out);  /* a cudaEvent_t */
+int b200rs_event_record(b200rs_device* dev, void* event);       /* on the handle's stream */
+/* Waits for stop_event, then *ms_out = device time between the two events. */
+int b200rs_event_elapsed_ms(b200rs_device* dev, void* start_event, void* stop_event, float* ms_out);
+int b200rs_event_destroy(b200rs_device* dev, void* event);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,10 @@ SIGNATURES = {
     "b200rs_sort_keys_u32": (_int, [c_dev, _vp, _u64, _int, _vp, _P(_sz)]),
     "b200rs_sort_pairs_u32": (_int, [c_dev, _vp, _u64, _int, _vp, _P(_sz)]),
     "b200rs_exclusive_scan_u32": (_int, [c_dev, _vp, _vp, _u64, _vp, _vp, _P(_sz)]),
+    "b200rs_copy_u32": (_int, [c_dev, _vp, _vp, _u64]),
+    "b200rs_copy_u128": (_int, [c_dev, _vp, _vp, _u64]),
+    "b200rs_fill_u32": (_int, [c_dev, _vp, ctypes.c_uint32, _u64]),
+    "b200rs_fill_u128": (_int, [c_dev, _vp, _P(ctypes.c_uint32), _u64]),
     "b200rs_digit_histogram_pairs": (_int, [c_dev, _vp, _u64, _int, _int, _vp]),
     "b200rs_partition_pairs": (_int, [c_dev, _vp, _vp, _u64, _int, _int, _vp, _vp, _vp, _P(_sz)]),
     "b200rs_scatter_pairs_to_parts": (_int, [c_dev, _vp, _u64, _int, _int, _vp, _vp, _vp, _vp, _P(_sz)]),
@@ -64,6 +68,10 @@ SIGNATURES = {
     "b200rs_profile_enable": (_int, [c_dev, _int]),
     "b200rs_profile_read": (_int, [c_dev, _P(ProfileEntry), _int, _P(_int)]),
     "b200rs_device_launch_count": (_int, [c_dev, _P(_u64)]),
+    "b200rs_event_create": (_int, [c_dev, _P(_vp)]),
+    "b200rs_event_record": (_int, [c_dev, _vp]),
+    "b200rs_event_elapsed_ms": (_int, [c_dev, _vp, _vp, _P(ctypes.c_float)]),
+    "b200rs_event_destroy": (_int, [c_dev, _vp]),
 }
 
 _lib = None

@@ -3,6 +3,8 @@
 // Plain C++ (no CUDA headers): link against libb200rs.so.
 #include <Tahoe/ParallelPrimitives/Pprims.h>
 
+#include <string.h>
+
 namespace Tahoe {
 
 namespace {
@@ -37,6 +39,62 @@ void* Pprims::reserveTemp(const adl::Device* device, size_t bytes) {
         device->m_memoryUsage += bytes;  // counted like any buffer so the teardown check stays meaningful
     }
     return m_temp;
+}
+
+// ---- copy / fill (reference: Pprims.cpp:31-121, PprimsKernels.cl:9-48) ----
+namespace {
+bool primArgsOk(const adl::Device* device, int n, u64 dstSize, u64 srcSize) {
+    if (!isGpuDevice(device) || n < 0) {
+        ADLASSERT(0);  // the reference's device == 0 branch is a CPU loop; there is no Host path here
+        return false;
+    }
+    ADLASSERT((u64)n <= dstSize && (u64)n <= srcSize);
+    return (u64)n <= dstSize && (u64)n <= srcSize;
+}
+}  // namespace
+
+void Pprims::copy(const adl::Device* device, adl::Buffer<int>& dst, const adl::Buffer<int>& src, int n) {
+    if (!primArgsOk(device, n, dst.getSize(), src.getSize())) return;
+    adl::adlCheck(b200rs_copy_u32(device->getHandle(), (uint32_t*)dst.m_ptr, (const uint32_t*)src.m_ptr, (uint64_t)n), "b200rs_copy_u32");
+}
+void Pprims::copy(const adl::Device* device, adl::Buffer<u32>& dst, const adl::Buffer<u32>& src, int n) {
+    if (!primArgsOk(device, n, dst.getSize(), src.getSize())) return;
+    adl::adlCheck(b200rs_copy_u32(device->getHandle(), (uint32_t*)dst.m_ptr, (const uint32_t*)src.m_ptr, (uint64_t)n), "b200rs_copy_u32");
+}
+void Pprims::copy(const adl::Device* device, adl::Buffer<float4>& dst, const adl::Buffer<float4>& src, int n) {
+    if (!primArgsOk(device, n, dst.getSize(), src.getSize())) return;
+    adl::adlCheck(b200rs_copy_u128(device->getHandle(), dst.m_ptr, src.m_ptr, (uint64_t)n), "b200rs_copy_u128");
+}
+void Pprims::fill(const adl::Device* device, adl::Buffer<int>& dst, int src, int n) {
+    if (!primArgsOk(device, n, dst.getSize(), (u64)n)) return;
+    adl::adlCheck(b200rs_fill_u32(device->getHandle(), (uint32_t*)dst.m_ptr, (uint32_t)src, (uint64_t)n), "b200rs_fill_u32");
+}
+void Pprims::fill(const adl::Device* device, adl::Buffer<u32>& dst, u32 src, int n) {
+    if (!primArgsOk(device, n, dst.getSize(), (u64)n)) return;
+    adl::adlCheck(b200rs_fill_u32(device->getHandle(), (uint32_t*)dst.m_ptr, src, (uint64_t)n), "b200rs_fill_u32");
+}
+void Pprims::fill(const adl::Device* device, adl::Buffer<float4>& dst, const float4& src, int n) {
+    if (!primArgsOk(device, n, dst.getSize(), (u64)n)) return;
+    uint32_t words[4];
+    memcpy(words, &src, sizeof(words));
+    adl::adlCheck(b200rs_fill_u128(device->getHandle(), dst.m_ptr, words, (uint64_t)n), "b200rs_fill_u128");
+}
+// uArray forms: the device copy is brought up to date and the CPU copy marked stale (uArray::getGpuBuffer), exactly
+// what setToLauncher did for the reference's launches (uArray.h:214-228).
+void Pprims::copy(const adl::Device* device, uArray<int>& dst, const uArray<int>& src, int n) {
+    copy(device, *const_cast<adl::Buffer<int>*>(dst.getGpuBuffer(device)), *src.getGpuBuffer(device), n);
+}
+void Pprims::copy(const adl::Device* device, uArray<float4>& dst, const uArray<float4>& src, int n) {
+    copy(device, *const_cast<adl::Buffer<float4>*>(dst.getGpuBuffer(device)), *src.getGpuBuffer(device), n);
+}
+void Pprims::fill(const adl::Device* device, uArray<int>& dst, int src, int n) {
+    fill(device, *const_cast<adl::Buffer<int>*>(dst.getGpuBuffer(device)), src, n);
+}
+void Pprims::fill(const adl::Device* device, uArray<u32>& dst, u32 src, int n) {
+    fill(device, *const_cast<adl::Buffer<u32>*>(dst.getGpuBuffer(device)), src, n);
+}
+void Pprims::fill(const adl::Device* device, uArray<float4>& dst, const float4& src, int n) {
+    fill(device, *const_cast<adl::Buffer<float4>*>(dst.getGpuBuffer(device)), src, n);
 }
 
 void Pprims::scan(const adl::Device* device, adl::Buffer<int>& dst, const adl::Buffer<int>& src, int n, u32* sumOut) {

@@ -223,15 +223,50 @@ int b200rs_profile_read(b200rs_device* dev, b200rs_profile_entry* out, int capac
     B200RS_CUDA(cudaStreamSynchronize(dev->stream));
     int n = 0;
     for (auto& s : dev->spans) {
+        if (n >= capacity) break;  // the rest stays queued for the next read
         float ms = 0.f;
         cudaEventElapsedTime(&ms, s.start, s.stop);
         s.entry.ms = ms;
-        if (n < capacity) out[n++] = s.entry;
+        out[n++] = s.entry;
         cudaEventDestroy(s.start);
         cudaEventDestroy(s.stop);
     }
-    dev->spans.clear();
+    dev->spans.erase(dev->spans.begin(), dev->spans.begin() + n);
     *count = n;
+    return B200RS_OK;
+}
+
+// ---- events: device-side interval timing for adl::Stopwatch (Adl/AdlStopwatch.h:27-83) -------------
+
+int b200rs_event_create(b200rs_device* dev, void** event_out) {
+    if (!dev || !event_out) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    cudaEvent_t e = nullptr;
+    B200RS_CUDA(cudaEventCreate(&e));
+    *event_out = (void*)e;
+    return B200RS_OK;
+}
+
+int b200rs_event_record(b200rs_device* dev, void* event) {
+    if (!dev || !event) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    B200RS_CUDA(cudaEventRecord((cudaEvent_t)event, dev->stream));
+    return B200RS_OK;
+}
+
+int b200rs_event_elapsed_ms(b200rs_device* dev, void* start_event, void* stop_event, float* ms_out) {
+    if (!dev || !start_event || !stop_event || !ms_out) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    B200RS_CUDA(cudaEventSynchronize((cudaEvent_t)stop_event));
+    B200RS_CUDA(cudaEventElapsedTime(ms_out, (cudaEvent_t)start_event, (cudaEvent_t)stop_event));
+    return B200RS_OK;
+}
+
+int b200rs_event_destroy(b200rs_device* dev, void* event) {
+    if (!dev) return B200RS_ERR_INVALID_ARGUMENT;
+    if (!event) return B200RS_OK;
+    b200rs_device_guard guard(dev);
+    B200RS_CUDA(cudaEventDestroy((cudaEvent_t)event));
     return B200RS_OK;
 }
 

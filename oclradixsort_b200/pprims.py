@@ -83,3 +83,32 @@ class Pprims:
         if sumOut:
             return int(self._word.read(1)[0])
         return None
+
+    def copy(self, device: Device, dst: Buffer, src: Buffer, n: int) -> None:
+        """Pprims::copy, Pprims.cpp:32-65 (CopyIntKernel / CopyF4Kernel, PprimsKernels.cl:9-24): dst[i] = src[i], i < n.
+        4-byte elements (int / u32) or 16-byte elements (float4).  Asynchronous."""
+        if device is None:
+            raise ValueError("device == 0: there is no Host path (reference: the CPU loop of Pprims.cpp:34-38)")
+        assert n <= dst.getSize() and n <= src.getSize() and dst.dtype.itemsize == src.dtype.itemsize
+        if dst.dtype.itemsize == 4:
+            check(lib().b200rs_copy_u32(device.handle, ctypes.c_void_p(dst.m_ptr), ctypes.c_void_p(src.m_ptr), n), "b200rs_copy_u32")
+        elif dst.dtype.itemsize == 16:
+            check(lib().b200rs_copy_u128(device.handle, ctypes.c_void_p(dst.m_ptr), ctypes.c_void_p(src.m_ptr), n), "b200rs_copy_u128")
+        else:
+            raise TypeError(f"unsupported element size {dst.dtype.itemsize}")
+
+    def fill(self, device: Device, dst: Buffer, value, n: int) -> None:
+        """Pprims::fill, Pprims.cpp:67-120 (FillIntKernel / FillU32Kernel / FillF4Kernel, PprimsKernels.cl:28-48):
+        dst[i] = value, i < n.  `value`: an int for 4-byte elements, 4 floats (or a 16-byte numpy scalar) for float4."""
+        if device is None:
+            raise ValueError("device == 0: there is no Host path (reference: the CPU loop of Pprims.cpp:69-73)")
+        assert n <= dst.getSize()
+        if dst.dtype.itemsize == 4:
+            word = int(np.asarray(value, dtype=dst.dtype).view(np.uint32)) if dst.dtype.kind != "u" else int(value) & 0xFFFFFFFF
+            check(lib().b200rs_fill_u32(device.handle, ctypes.c_void_p(dst.m_ptr), word, n), "b200rs_fill_u32")
+        elif dst.dtype.itemsize == 16:
+            raw = np.asarray(value, dtype=np.float32).reshape(4) if not isinstance(value, np.void) else np.frombuffer(value.tobytes(), np.float32)
+            words = (ctypes.c_uint32 * 4)(*[int(w) for w in raw.view(np.uint32)])
+            check(lib().b200rs_fill_u128(device.handle, ctypes.c_void_p(dst.m_ptr), words, n), "b200rs_fill_u128")
+        else:
+            raise TypeError(f"unsupported element size {dst.dtype.itemsize}")

@@ -150,3 +150,17 @@ def ref_time_hostbackend(data: np.ndarray, pairs: bool) -> float:
     assert data.flags["C_CONTIGUOUS"]
     fn = ref().ref_hostbackend_sort_pairs_timed if pairs else ref().ref_hostbackend_sort_u32_timed
     return float(fn(_ptr(data), data.shape[0]))
+
+
+def copy_elems(dst: np.ndarray, src: np.ndarray, n: int) -> np.ndarray:
+    """Pprims::copy's CPU loop `for i<n: dst[i] = src[i]` (Pprims.cpp:34-38, :51-55); returns the new dst."""
+    out = dst.copy()
+    out[:n] = src[:n]
+    return out
+
+
+def fill_elems(dst: np.ndarray, value, n: int) -> np.ndarray:
+    """Pprims::fill's CPU loop `for i<n: dst[i] = src` (Pprims.cpp:69-73, :86-90, :103-107); returns the new dst."""
+    out = dst.copy()
+    out[:n] = value
+    return out
