@@ -21,7 +21,7 @@ all: $(LIB) $(TAHOE_LIB)
 $(TAHOE_LIB): $(CSRC)/Pprims.cpp $(LIB) $(wildcard include/Adl/*.h include/Tahoe/*/*.h include/Tahoe/*/*/*.h)
 	$(CXX) -std=c++11 -O2 -Wall -fPIC -shared -Iinclude $(CSRC)/Pprims.cpp -Loclradixsort_b200 -lb200rs -Wl,-rpath,'$$ORIGIN' -o $@
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/b200rs_internal.h include/b200rs.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/b200rs_internal.h include/b200rs.h $(wildcard $(CSRC)/*.cuh)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(@:.o=.ptxas.log) || (cat $(@:.o=.ptxas.log); false)
 
 $(LIB): $(OBJS)

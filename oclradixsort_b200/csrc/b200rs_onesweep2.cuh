@@ -156,6 +156,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
         ::"r"(mbar), "r"(parity)
         : "memory");
 }
+// One instruction pulls `bytes` (multiple of 16, 16-byte aligned source) into L2; nothing waits for it.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint32_t lanemask_le() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
@@ -300,7 +304,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
                  const unsigned long long* __restrict__ digit_start /*[RADIX]: exclusive scan of the pass's histogram*/, Lookback3 lb,
                  uint32_t* ticket, uint32_t pass, uint32_t minus_one /* 0xffffffff, opaque to ptxas: see same_digit_lanes */,
-                 const unsigned long long* __restrict__ n_dev, const uint32_t* __restrict__ pass_ctl) {
+                 const unsigned long long* __restrict__ n_dev, const uint32_t* __restrict__ pass_ctl,
+                 uint32_t pf_tiles /* L2 prefetch distance in tiles (about the number of co-resident CTAs); 0 = off */) {
     using Cfg = Onesweep2Config<ElemT, THREADS, IPT, WO>;
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -317,6 +322,12 @@ onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t
         s.tile = t;
         s.ctl = ctl;
         s.n_eff = n_eff;
+        // The CTA that will take over this CTA's slot gets a ticket about pf_tiles higher: pull that tile into L2 now
+        // (one bulk prefetch, nobody waits for it), so its counting phase sees L2 latency instead of HBM latency.
+        if (pf_tiles && in_aligned) {
+            const uint64_t pf_base = ((uint64_t)t + pf_tiles) * Cfg::TILE;
+            if (pf_base + Cfg::TILE <= n_eff) bulk_prefetch_l2(in + pf_base, Cfg::TILE * (uint32_t)sizeof(ElemT));
+        }
         if (LOAD == LOAD_BULK) {
             const uint32_t mbar = smem_addr(&s.mbar);
             mbar_init(mbar, 1);

@@ -480,6 +480,7 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
 }
 
 #include "b200rs_onesweep2.cuh"
+#include "b200rs_onesweep3.cuh"
 
 // ---- host side -------------------------------------------------------------------------------------
 
@@ -489,14 +490,17 @@ struct Variant {
     int threads, ipt;
     size_t smem;
     const char* name;
-    int gen;  // 1: onesweep_kernel (tagged per-digit look-back), 2: onesweep2_kernel (per-tile flags, bulk write-out)
+    int gen;  // 1: onesweep_kernel (tagged per-digit look-back), 2: onesweep2_kernel (two-level look-back), 3: onesweep3_kernel (persistent)
+    int ctas_per_sm;  // generation 3: the grid is min(tiles, SMs x ctas_per_sm) persistent CTAs
 };
 #define B200RS_VARIANT(ElemT, THREADS, IPT, MODE, MIN_CTAS) \
-    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS, 1}
+    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS, 1, 0}
 #define B200RS_VARIANT_W(ElemT, THREADS, IPT, MODE, MIN_CTAS, W) \
-    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS, false, false, W>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS "w" #W, 1}
+    Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS, false, false, W>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS "w" #W, 1, 0}
 #define B200RS_VARIANT2(ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER, LOAD) \
-    Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER, LOAD>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":" #WO ":" #ORDER ":" #LOAD, 2}
+    Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER, LOAD>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":" #WO ":" #ORDER ":" #LOAD, 2, 0}
+#define B200RS_VARIANT3(ElemT, THREADS, IPT, MIN_CTAS, PF) \
+    Variant{(const void*)onesweep3_kernel<ElemT, THREADS, IPT, MIN_CTAS, PF>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO_ELEM>::Smem), "v3:" #THREADS "x" #IPT "/" #MIN_CTAS ":persistent:pf" #PF, 3, MIN_CTAS}
 
 template <typename ElemT> struct Variants;
 template <> struct Variants<uint32_t> {
@@ -536,6 +540,8 @@ template <> struct Variants<uint32_t> {
             B200RS_VARIANT2(uint32_t, 256, 48, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 31
             B200RS_VARIANT2(uint32_t, 256, 36, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 32
             B200RS_VARIANT2(uint32_t, 256, 32, 4, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 33
+            B200RS_VARIANT3(uint32_t, 256, 32, 4, 1),  // 34  measurement: persistent CTAs + L2 prefetch of the next tile (0.75 ms/pass vs 0.66)
+            B200RS_VARIANT3(uint32_t, 256, 32, 4, 0),  // 35  measurement: persistent CTAs only (0.80 ms/pass)
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
@@ -569,6 +575,8 @@ template <> struct Variants<uint2> {
             B200RS_VARIANT2(uint2, 256, 24, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 20 (= 14)
             B200RS_VARIANT2(uint2, 320, 20, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 21
             B200RS_VARIANT2(uint2, 288, 24, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 22
+            B200RS_VARIANT3(uint2, 384, 16, 3, 1),  // 23  measurement: persistent CTAs + L2 prefetch of the next tile (1.05 ms/pass vs 0.99)
+            B200RS_VARIANT3(uint2, 384, 16, 3, 0),  // 24  measurement: persistent CTAs only (1.15 ms/pass)
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
@@ -646,7 +654,7 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     const size_t partial_bytes = b200rs_align_up((size_t)num_tiles * RADIX * sizeof(uint32_t), 256);
     const size_t num_groups = ((size_t)num_tiles + LB_GROUP - 1) / LB_GROUP;
     const size_t clear_bytes = (plan.lookback_off - plan.clear_off) +
-                               (var.gen == 2 ? partial_bytes + num_groups * RADIX * sizeof(uint64_t) : (size_t)num_tiles * RADIX * sizeof(uint64_t));
+                               (var.gen >= 2 ? partial_bytes + num_groups * RADIX * sizeof(uint64_t) : (size_t)num_tiles * RADIX * sizeof(uint64_t));
     B200RS_CUDA(cudaMemsetAsync(base + plan.clear_off, 0, clear_bytes, dev->stream));
     Lookback3 lb2;
     lb2.partial = reinterpret_cast<uint32_t*>(base + plan.lookback_off);
@@ -674,12 +682,18 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     }
     B200RS_CUDA(cudaGetLastError());
     uint32_t* pass_ctl = tickets + 32;  // [passes], inside the zeroed ticket block
-    if (var.gen == 2) {
+    if (var.gen >= 2) {
         b200rs_launch_scope scope(dev, "digit_start", (uint64_t)plan.passes * RADIX, (uint64_t)plan.passes * RADIX * 16);
         digit_start_kernel<<<1, RADIX, 0, dev->stream>>>(ghist, plan.passes, n, n_dev, pass_ctl);
     }
 
     B200RS_CUDA(cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
+    // L2 prefetch distance of the scatter pass, in tiles.  Tickets are handed out at ~40 tiles per microsecond, so 64 tiles
+    // ahead is ~1.5 us, longer than an HBM round trip; measured flat from 32 to 222 tiles (pairs 0.992 ms/pass against
+    // 1.046 without), worse again from ~600 tiles on (the prefetched lines are evicted before use: 1.11 ms at 888).
+    // B200RS_PF_TILES overrides (development knob; 0 switches the prefetch off).
+    uint32_t pf_tiles = var.gen == 2 ? 64u : 0u;
+    if (const char* e = getenv("B200RS_PF_TILES")) pf_tiles = (uint32_t)atoi(e);
     ElemT* src = inout;
     ElemT* dst = alt;
     for (int p = 0; p < plan.passes; ++p) {
@@ -694,11 +708,13 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         uint32_t minus_one = 0xffffffffu;
         uint32_t pass = (uint32_t)p;
         void* args1[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lookback, &ticket, &tag_base, &no_lut, &n_dev, &minus_one};
-        void* args2[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lb2, &ticket, &pass, &minus_one, &n_dev, &pass_ctl};  // ghist_pass: pre-scanned
+        void* args2[] = {&src, &dst, &n_arg, &shift, &digit_mask, &ghist_pass, &lb2, &ticket, &pass, &minus_one, &n_dev, &pass_ctl, &pf_tiles};  // ghist_pass: pre-scanned
         snprintf(label, sizeof(label), "onesweep_%s_pass%d", what, p);
         {
             b200rs_launch_scope scope(dev, label, n, 2ull * n * sizeof(ElemT));
-            B200RS_CUDA(cudaLaunchKernel(var.kernel, dim3(num_tiles), dim3(var.threads), var.gen == 2 ? args2 : args1, var.smem, dev->stream));
+            uint32_t grid = num_tiles;
+            if (var.gen == 3 && grid > (uint32_t)(dev->num_sms * var.ctas_per_sm)) grid = (uint32_t)(dev->num_sms * var.ctas_per_sm);
+            B200RS_CUDA(cudaLaunchKernel(var.kernel, dim3(grid), dim3(var.threads), var.gen >= 2 ? args2 : args1, var.smem, dev->stream));
         }
         ElemT* t = src; src = dst; dst = t;
     }
