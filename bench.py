@@ -314,7 +314,7 @@ def main() -> None:
                     traffic = json.load(f).get(f"onesweep_pairs_dram_bytes_per_launch_2^{args.log2_pairs_per_gpu}")
             except Exception:
                 pass
-            roofline = {"bound": "hbm", "kernel": "onesweep2_kernel<uint2, 384 threads x 16 pairs> (one scatter pass, 4 per sort)", "achieved": achieved, "peak": peak,
+            roofline = {"bound": "hbm", "kernel": "onesweep2_kernel<uint2, 320 threads x 20 pairs> (one scatter pass, 4 per sort)", "achieved": achieved, "peak": peak,
                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": scatter[0]["bytes"],
                         "whole_sort": {"algorithmic_bytes": 72 * n, "achieved": 72 * n / (ms_per_step * 1e-3) / 1e9,

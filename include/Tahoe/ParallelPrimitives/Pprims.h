@@ -26,8 +26,8 @@ public:
         RSORT_BITS_PER_PASS = 8,
         RSORT_NUM_TABLES = (1 << RSORT_BITS_PER_PASS),
         R32SORT_DATA_ALIGNMENT = 1,       // any n (the reference's key-only kernels needed multiples of 256)
-        R32SORT_WG_SIZE = 512,
-        R32SORT_ELEMENTS_PER_WORK_ITEM = 24,
+        R32SORT_WG_SIZE = 256,
+        R32SORT_ELEMENTS_PER_WORK_ITEM = 35,
         R32SORT_BITS_PER_PASS = 8,        // the reference's device path used 4
     };
 

@@ -43,7 +43,7 @@ struct Onesweep2Config {
     static constexpr int M = WO == WO_BULK ? 16 / (int)sizeof(ElemT) : 1;         // elements per 16-byte chunk
     static constexpr int STAGE_SLOTS = TILE + (M > 1 ? 2 * (M - 1) * RADIX : 0);  // every run may be padded at both ends
     struct Smem {
-        alignas(16) ElemT staged[STAGE_SLOTS];  // tile in sorted order; run d starts at a slot congruent to its global index mod M
+        alignas(128) ElemT staged[STAGE_SLOTS];  // tile in sorted order; run d starts at a slot congruent to its global index mod M
         uint32_t warp_offset[WARPS][RADIX];     // per-warp digit counts -> running staged slot of (warp, digit)
         uint64_t run_ptr[RADIX];                // WO_ELEM: byte address in `out` of staged slot 0, as seen by digit d's run
         uint64_t mbar;                          // LOAD_BULK: completion of the tile's bulk copy
@@ -166,7 +166,13 @@ __device__ __forceinline__ uint32_t lanemask_le() {
     return m;
 }
 
-template <typename ElemT, int THREADS, int IPT, int WO, int ORDER, int LOAD, bool FULL, bool BYTE_DIGIT>
+// SWZ: the staged tile is stored with the bank bits of every element's shared-memory address XORed with a hash of its
+// 128-byte row number (a permutation inside each row, so still a bijection).  Without it the slot of an element is
+// run start + fill count, and inputs whose digits are evenly spread -- presorted or reversed keys k*i, any arithmetic
+// progression -- make every run of a tile the same length C: lanes holding different digits then hit addresses that differ
+// by multiples of C, and with C = 32 words (256 threads x 32 keys / 256 digits) all 32 lanes of a scatter store land in ONE
+// bank (measured: 1.30 ms per pass against 0.66 for uniform keys).  The hash decorrelates bank and run start for any C.
+template <typename ElemT, int THREADS, int IPT, int WO, int ORDER, int LOAD, bool FULL, bool BYTE_DIGIT, int SWZ>
 __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, THREADS, IPT, WO>::Smem& s, const ElemT* __restrict__ in,
                                                ElemT* __restrict__ out, uint64_t tile_base, uint32_t valid, int shift,
                                                uint32_t digit_mask, uint32_t prmt_sel, uint32_t tile, uint32_t pass,
@@ -180,6 +186,9 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
     const uint32_t slice = warp * Cfg::WARP_SLICE + lane;  // tile-local index of item 0
     const uint32_t my_offset = smem_addr(&s.warp_offset[warp][0]);
     const uint32_t staged = smem_addr(&s.staged[0]);
+    constexpr bool SWIZZLE = SWZ != 0 && WO == WO_ELEM;
+    constexpr uint32_t SWZ_MASK = E == 4 ? 0x7cu : 0x78u;  // address bits that select the element inside its 128-byte row
+    auto swz = [&](uint32_t a) { return SWIZZLE ? a ^ ((((a >> 7) * 0x9E3779B1u) >> 25) & SWZ_MASK) : a; };
 
     // ---- 1. warp-striped load + per-warp digit counts ----
     ElemT elem[IPT];
@@ -249,7 +258,7 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
         const bool leader = (peers & gt) == 0 && live;
         uint32_t base = atom_add_shared(leader ? my_offset + 4u * digit : dummy, upto);
         base = __shfl_sync(0xffffffffu, base, 31 - __clz(peers));
-        if (live) st_shared(base + upto, elem[i]);
+        if (live) st_shared(swz(base + upto), elem[i]);
     }
 
     // ---- 4. write-out ----
@@ -278,28 +287,33 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
         if (tid < RADIX) {
             if (ORDER == ORDER_LATE) exclusive = (uint64_t)digit_start[tid] + lookback3_resolve(lb, tile, pass, total, mates, tid);
             // (a 32-bit element-index table + IMAD.WIDE per element was measured 5-6 % slower than this 64-bit pointer table)
-            s.run_ptr[tid] = (uint64_t)(uintptr_t)(out + exclusive) - (uint64_t)sbase * E;
+            // SWIZZLE: the write-out adds the element's (un-swizzled) absolute shared address, so `staged` is taken off here
+            s.run_ptr[tid] = (uint64_t)(uintptr_t)(out + exclusive) - (uint64_t)sbase * E - (SWIZZLE ? (uint64_t)staged : 0ull);
         }
         __syncthreads();
         {
             const uint64_t my_bytes = (uint64_t)tid * E;
+            const uint32_t my_addr = staged + (uint32_t)tid * E;  // physical position tid of the staged tile
 #pragma unroll
             for (int k = 0; k < IPT; ++k) {
-                const uint32_t j = (uint32_t)tid + (uint32_t)k * THREADS;
-                if (FULL || j < valid) {
+                const uint32_t j = (uint32_t)tid + (uint32_t)k * THREADS;  // physical position read by this thread
+                // its logical slot (position in sorted order), as an absolute shared address: the swizzle is its own inverse
+                const uint32_t logical = swz(my_addr + (uint32_t)k * THREADS * E);
+                if (FULL || (SWIZZLE ? (logical - staged) / E : j) < valid) {
                     const ElemT e = s.staged[j];
                     const uint32_t d = digit_of<BYTE_DIGIT>(Elem<ElemT>::key(e), shift, digit_mask, prmt_sel);
                     // A plain C++ store through a pointer rebuilt from an integer compiles to a GENERIC store (ST.E), and
                     // that is deliberate: telling the compiler the address is global (__isGlobal / st.global) lets it hoist
                     // all of the loop's shared-memory reads above the stores, which measured 4 % slower (keys and pairs).
-                    *reinterpret_cast<ElemT*>(s.run_ptr[d] + my_bytes + (uint64_t)k * THREADS * E) = e;
+                    if (SWIZZLE) *reinterpret_cast<ElemT*>(s.run_ptr[d] + (uint64_t)logical) = e;
+                    else         *reinterpret_cast<ElemT*>(s.run_ptr[d] + my_bytes + (uint64_t)k * THREADS * E) = e;
                 }
             }
         }
     }
 }
 
-template <typename ElemT, int THREADS, int IPT, int MIN_CTAS, int WO, int ORDER, int LOAD>
+template <typename ElemT, int THREADS, int IPT, int MIN_CTAS, int WO, int ORDER, int LOAD, int SWZ = 0>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
                  const unsigned long long* __restrict__ digit_start /*[RADIX]: exclusive scan of the pass's histogram*/, Lookback3 lb,
@@ -308,7 +322,7 @@ onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t
                  uint32_t pf_tiles /* L2 prefetch distance in tiles (about the number of co-resident CTAs); 0 = off */) {
     using Cfg = Onesweep2Config<ElemT, THREADS, IPT, WO>;
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(smem_raw);
     // Thread 0 fetches, concurrently, the tile ticket, the pass control word (digit_start_kernel: PASS_IDENTITY = every
     // element has the same digit in this pass, so the pass moves nothing) and the device-side element count (multi-GPU
@@ -364,10 +378,10 @@ onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t
     const uint32_t prmt_sel = 0x4440u | (uint32_t)(shift >> 3);
 
     if (valid == Cfg::TILE) {
-        if (byte_digit) onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, true, true>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, in_aligned);
-        else            onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, true, false>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, in_aligned);
+        if (byte_digit) onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, true, true, SWZ>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, in_aligned);
+        else            onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, true, false, SWZ>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, in_aligned);
     } else {
-        onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, false, false>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, false);
+        onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, false, false, SWZ>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, false);
     }
 }
 

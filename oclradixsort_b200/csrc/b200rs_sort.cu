@@ -499,6 +499,8 @@ struct Variant {
     Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS, false, false, W>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS "w" #W, 1, 0}
 #define B200RS_VARIANT2(ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER, LOAD) \
     Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER, LOAD>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":" #WO ":" #ORDER ":" #LOAD, 2, 0}
+#define B200RS_VARIANT2S(ElemT, THREADS, IPT, MIN_CTAS) \
+    Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO_ELEM, ORDER_LATE, LOAD_LDG, 1>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO_ELEM>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":swizzled", 2, 0}
 #define B200RS_VARIANT3(ElemT, THREADS, IPT, MIN_CTAS, PF) \
     Variant{(const void*)onesweep3_kernel<ElemT, THREADS, IPT, MIN_CTAS, PF>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO_ELEM>::Smem), "v3:" #THREADS "x" #IPT "/" #MIN_CTAS ":persistent:pf" #PF, 3, MIN_CTAS}
 
@@ -542,12 +544,22 @@ template <> struct Variants<uint32_t> {
             B200RS_VARIANT2(uint32_t, 256, 32, 4, WO_ELEM, ORDER_LATE, LOAD_BULK),  // 33
             B200RS_VARIANT3(uint32_t, 256, 32, 4, 1),  // 34  measurement: persistent CTAs + L2 prefetch of the next tile (0.75 ms/pass vs 0.66)
             B200RS_VARIANT3(uint32_t, 256, 32, 4, 0),  // 35  measurement: persistent CTAs only (0.80 ms/pass)
+            B200RS_VARIANT2(uint32_t, 256, 33, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 36  odd keys-per-digit average: see the note on structured inputs
+            B200RS_VARIANT2(uint32_t, 256, 31, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 37
+            B200RS_VARIANT2(uint32_t, 256, 35, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 38
+            B200RS_VARIANT2(uint32_t, 256, 29, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 39
+            B200RS_VARIANT2S(uint32_t, 256, 32, 4),  // 40  staged tile swizzled
+            B200RS_VARIANT2S(uint32_t, 256, 35, 4),  // 41
+            B200RS_VARIANT2S(uint32_t, 256, 36, 4),  // 42
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
     }
     static const char* env() { return "B200RS_KEYS_VARIANT"; }
-    static int default_index() { return 25; }  // 256 threads x 32 keys, 4 CTAs/SM
+    // 256 threads x 35 keys, 4 CTAs/SM.  35 and not 32: with evenly spread digits (presorted / reversed / strided keys) every
+    // run of the staged tile is TILE/256 slots long, and a multiple of 32 words puts all lanes of a scatter store into
+    // one shared-memory bank (256x32: 1.30 ms per pass on presorted keys, 256x35: 0.58; uniform keys: 0.66 both)
+    static int default_index() { return 38; }
 };
 template <> struct Variants<uint2> {
     static const Variant* list(int* count) {
@@ -577,14 +589,21 @@ template <> struct Variants<uint2> {
             B200RS_VARIANT2(uint2, 288, 24, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 22
             B200RS_VARIANT3(uint2, 384, 16, 3, 1),  // 23  measurement: persistent CTAs + L2 prefetch of the next tile (1.05 ms/pass vs 0.99)
             B200RS_VARIANT3(uint2, 384, 16, 3, 0),  // 24  measurement: persistent CTAs only (1.15 ms/pass)
+            B200RS_VARIANT2(uint2, 384, 18, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 25  27 pairs per digit on average (odd)
+            B200RS_VARIANT2(uint2, 384, 14, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 26  21
+            B200RS_VARIANT2(uint2, 256, 23, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 27  23
+            B200RS_VARIANT2(uint2, 256, 25, 3, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 28  25
+            B200RS_VARIANT2(uint2, 256, 21, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 29  21
+            B200RS_VARIANT2S(uint2, 384, 16, 3),  // 30  staged tile swizzled
+            B200RS_VARIANT2S(uint2, 320, 20, 3),  // 31
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
     }
     static const char* env() { return "B200RS_PAIRS_VARIANT"; }
-    static int default_index() { return 8; }
+    static int default_index() { return 21; }  // 320 threads x 20 pairs = 25 pairs per digit on average (odd, see the keys note), 3 CTAs/SM
 };
-constexpr uint64_t MIN_TILE = 384 * 16;  // smallest tile among the variants: temp storage is sized for it
+constexpr uint64_t MIN_TILE = 256 * 21;  // smallest tile among the variants: temp storage is sized for it
 
 template <typename ElemT>
 const Variant& pick_variant() {

@@ -48,12 +48,17 @@ def main():
                     e0.record(st); p.radixSort(d, buf, n, bits); e1.record(st); st.synchronize()
                     ts.append(e0.elapsed_time(e1))
                 t = min(ts[1:])
+                per_kernel = ""
+                if os.environ.get("B200RS_TOOL_PROFILE"):  # per-kernel times of one more (untimed) sort
+                    work.copy_(src); d.toggleProfiling(True); p.radixSort(d, buf, n, bits)
+                    per_kernel = " " + ", ".join(f"{e['kernel'].replace('onesweep_keys_', '').replace('digit_', '')} {e['ms']:.3f}" for e in d.readProfile())
+                    d.toggleProfiling(False)
                 mask = (1 << bits) - 1
                 k = work.to(torch.int64) & mask
                 ok = bool((k[1:] >= k[:-1]).all()) and int(work.to(torch.int64).sum().item()) == int(src.to(torch.int64).sum().item())
                 del k
                 bpk = 4 + 8 * ((bits + 7) // 8)
-                print(f"| 2^{log2n} | {kind} | {bits} | {t:.3f} | {n/t/1e6:.1f} | {n*bpk/t/1e6/PEAK:.1%} |{'' if ok else ' WRONG'}", flush=True)
+                print(f"| 2^{log2n} | {kind} | {bits} | {t:.3f} | {n/t/1e6:.1f} | {n*bpk/t/1e6/PEAK:.1%} |{'' if ok else ' WRONG'}{per_kernel}", flush=True)
                 del src, work
         p.release()
 

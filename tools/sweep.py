@@ -11,8 +11,12 @@ PEAK = 6555.2
 def main():
     log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 28
     sel = {"keys": [0], "pairs": [0], "scan": [0]}
+    dist = "uniform"
     for a in sys.argv[2:]:
         k, v = a.split("=")
+        if k == "dist":
+            dist = v  # uniform | sorted (key = i * 2^32/n, pairs: value = i)
+            continue
         sel[k] = [int(x) for x in v.split(",")] if v else []
     n = 1 << log2n
     torch.cuda.set_device(0)
@@ -25,6 +29,9 @@ def main():
             if not sel[what]:
                 continue
             src = torch.randint(-2**31, 2**31, (n, width), device="cuda", dtype=torch.int32, generator=g)
+            if dist == "sorted":
+                src[:, 0] = (torch.arange(n, device="cuda", dtype=torch.int64) * (2**32 // n)).to(torch.int32)
+                if width == 2: src[:, 1] = torch.arange(n, device="cuda", dtype=torch.int32)
             work = torch.empty_like(src)
             ref = None
             buf = ob.Buffer(d, n, np.uint32 if width == 1 else ob.PAIR_DTYPE, ptr=work.data_ptr())
@@ -44,7 +51,7 @@ def main():
                 else: ok = "same" if torch.equal(ref, work) else "DIFFERENT"
                 t = min(times[1:5]); bpk = 36 * width
                 ks = ", ".join(f"{e['kernel'].split('_')[0]}{e['kernel'][-1]} {e['ms']:.3f}" for e in prof)
-                print(f"{what} v{v} 2^{log2n}: {t:.3f} ms {n/t/1e6:.1f} Gelem/s {n*bpk/t/1e6/PEAK:.1%} [{ks}] {ok}", flush=True)
+                print(f"{what} v{v} {dist} 2^{log2n}: {t:.3f} ms {n/t/1e6:.1f} Gelem/s {n*bpk/t/1e6/PEAK:.1%} [{ks}] {ok}", flush=True)
             os.environ.pop(env, None)
             del src, work, ref
         if sel["scan"]:
