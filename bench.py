@@ -100,7 +100,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def reference_arm(args, rank: int) -> None:
+def reference_arm(args, rank: int, json_out) -> None:
     """The reference's own CPU implementation of the path, timed on this box's host cores."""
     if rank != 0:
         return
@@ -136,7 +136,7 @@ def reference_arm(args, rank: int) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
 
 
 def cpu_baseline(log2_sample: int):
@@ -178,8 +178,15 @@ def main() -> None:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    # Contract: rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." on stdout
+    # when NCCL_DEBUG=VERSION, as on the GPU boxes), so file descriptor 1 is pointed at stderr for the whole run and the
+    # JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     if args.impl == "reference":
-        reference_arm(args, rank)
+        reference_arm(args, rank, json_out)
         return
 
     import numpy as np
@@ -400,7 +407,7 @@ def main() -> None:
         }
         if extras:
             line["extra"] = extras
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
