@@ -235,6 +235,8 @@ def main() -> None:
             else:
                 last["out"] = sorter.sort_async(inputs64[i], n)  # stream-ordered: no host round trip inside a step
 
+        sampler = ClockSampler(local_rank)  # NVML is initialised here, well before the timed region: with 8 ranks doing it at once
+        #                                     right before the first timed step, that step took 12.9 ms instead of 8.1
         for i in range(args.warmup):
             step(i)
         stream.synchronize()
@@ -242,7 +244,6 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
         launches0 = dev.launch_count()
-        sampler = ClockSampler(local_rank)
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]

@@ -42,6 +42,10 @@ def _keys(kind: str, n: int, seed: int = 1) -> np.ndarray:
         return np.sort(u)
     if kind == "reversed":
         return np.sort(u)[::-1].copy()
+    if kind == "strided":  # presorted arithmetic progression c*i (BASELINE config 4): every digit equally frequent in every tile
+        return (np.arange(n, dtype=np.uint64) * np.uint64(2**32 // max(n, 1))).astype(np.uint32)
+    if kind == "strided_reversed":
+        return (np.arange(n, dtype=np.uint64) * np.uint64(2**32 // max(n, 1))).astype(np.uint32)[::-1].copy()
     if kind == "and3":
         a = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
         b = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
@@ -49,8 +53,8 @@ def _keys(kind: str, n: int, seed: int = 1) -> np.ndarray:
     raise ValueError(kind)
 
 
-SIZES = [1, 2, 31, 32, 33, 255, 256, 257, 1000, 4095, 4096, 4097, 8191, 8192, 8193, 100003, 1 << 20, (1 << 22) + 7]
-KINDS = ["uniform", "lowbyte", "few", "allequal", "allmax", "sorted", "reversed", "and3"]
+SIZES = [1, 2, 31, 32, 33, 255, 256, 257, 1000, 4095, 4096, 4097, 6399, 6400, 6401, 8191, 8192, 8193, 8959, 8960, 8961, 100003, 1 << 20, (1 << 22) + 7]
+KINDS = ["uniform", "lowbyte", "few", "allequal", "allmax", "sorted", "reversed", "and3", "strided", "strided_reversed"]
 
 
 def _sort_keys(ctx, keys, bits=32):
@@ -113,17 +117,18 @@ def test_sort_pairs_stability(ctx, kind):
 
 
 # The scatter pass groups tiles by 8 for its two-level look-back (csrc/b200rs_onesweep2.cuh, LB_GROUP); tiles are
-# 8192 keys / 6144 pairs.  Sizes around whole groups, one tile more, one element less, and several groups deep.
+# 8960 keys / 6400 pairs (8192 / 6144 / 10240 in earlier defaults, still selectable).  Sizes around whole groups, one
+# tile more, one element less, and several groups deep.
 GROUP_EDGE_TILES = [7, 8, 9, 16, 17, 41]
 
 
 @pytest.mark.parametrize("tiles", GROUP_EDGE_TILES)
 def test_sort_lookback_group_boundaries(ctx, tiles):
     ob = ctx[0]
-    for n in (tiles * 8192 - 1, tiles * 8192, tiles * 8192 + 1, tiles * 10240 + 1):
+    for n in (tiles * 8960 - 1, tiles * 8960, tiles * 8960 + 1, tiles * 8192 - 1, tiles * 8192, tiles * 8192 + 1, tiles * 10240 + 1):
         k = _keys("and3", n)  # low entropy: long equal-key runs cross tile and group edges
         assert np.array_equal(_sort_keys(ctx, k), po.sort_u32(k)), n
-    for n in (tiles * 6144 - 1, tiles * 6144, tiles * 6144 + 1):
+    for n in (tiles * 6400 - 1, tiles * 6400, tiles * 6400 + 1, tiles * 6144 - 1, tiles * 6144, tiles * 6144 + 1):
         kv = np.empty(n, dtype=ob.PAIR_DTYPE)
         kv["key"], kv["value"] = _keys("few", n), np.arange(n, dtype=np.uint32)
         assert np.array_equal(_sort_pairs(ctx, kv), po.sort_pairs(kv)), n
