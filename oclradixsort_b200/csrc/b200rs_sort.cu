@@ -153,6 +153,67 @@ digit_histogram_kernel(const ElemT* __restrict__ in, uint64_t n, uint32_t key_ma
     drain();
 }
 
+// Variant with one 32-bit counter per (digit, lane): the 16-bit packing above costs two instructions per digit
+// (PRMT + IMAD to build the increment) in a kernel that is bound by instruction issue (27 warp instructions per 32 keys,
+// issue slots 73 % busy, HBM 61 %).  Here a digit costs SHF + LOP3 + ATOMS: 13 instructions per key instead of 21.  The
+// table is [NUM_PASSES][256 digits][32 lanes] words = 32 KiB per digit place, so one 1024-thread CTA per SM; a counter
+// cannot overflow (a lane sees fewer than 2^32 keys), so the table is drained once, at the end.
+constexpr int HIST32_THREADS = 1024;
+template <typename ElemT, int NUM_PASSES>
+__global__ void __launch_bounds__(HIST32_THREADS, 1)
+digit_histogram32_kernel(const ElemT* __restrict__ in, uint64_t n, uint32_t key_mask, unsigned long long* __restrict__ ghist /*[num_passes][RADIX]*/,
+                         const unsigned long long* __restrict__ n_dev) {
+    extern __shared__ __align__(16) uint32_t s_cnt[];  // [NUM_PASSES][RADIX][32 lanes]
+    if (n_dev) n = min(n, (uint64_t)*n_dev);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < NUM_PASSES * RADIX * 32; i += HIST32_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+
+    constexpr int KEYS_PER_VEC = 16 / sizeof(ElemT);
+    const uint64_t nvec = n / KEYS_PER_VEC;
+    const uint4* in4 = reinterpret_cast<const uint4*>(in);
+    const uint32_t table = smem_addr(s_cnt);  // CTA-uniform
+    const uint32_t col = 4u * lane;           // this lane's column: word (place p, digit d, lane l) sits in bank l
+    auto count = [&](uint32_t key) {
+        key &= key_mask;
+#pragma unroll
+        for (int p = 0; p < NUM_PASSES; ++p) {
+            uint32_t off;  // digit * 128 | col in one LOP3: the shifted key has the digit at bits 7..14
+            asm("lop3.b32 %0, %1, 0x7f80, %2, 0xea;" : "=r"(off) : "r"(p == 0 ? key << 7 : key >> (8 * p - 7)), "r"(col));
+            red_add_shared(table + off + (uint32_t)p * (RADIX * 128u), 1u);
+        }
+    };
+    const uint64_t round_vecs = (uint64_t)HIST32_THREADS * HIST_VEC_PER_THREAD;
+    for (uint64_t base = (uint64_t)blockIdx.x * round_vecs; base < nvec; base += (uint64_t)gridDim.x * round_vecs) {
+        uint4 q[HIST_VEC_PER_THREAD];
+        bool have[HIST_VEC_PER_THREAD];
+#pragma unroll
+        for (int u = 0; u < HIST_VEC_PER_THREAD; ++u) {
+            const uint64_t v = base + (uint64_t)u * HIST32_THREADS + tid;
+            have[u] = v < nvec;
+            if (have[u]) q[u] = __ldg(in4 + v);
+        }
+#pragma unroll
+        for (int u = 0; u < HIST_VEC_PER_THREAD; ++u)
+            if (have[u]) {
+                if (sizeof(ElemT) == 4) { count(q[u].x); count(q[u].y); count(q[u].z); count(q[u].w); }
+                else                    { count(q[u].x); count(q[u].z); }
+            }
+    }
+    if (blockIdx.x == 0) {  // ragged tail (n not a multiple of the vector width)
+        const uint64_t i = nvec * KEYS_PER_VEC + tid;
+        if (i < n) count(Elem<ElemT>::key(in[i]));
+    }
+    __syncthreads();
+    // drain: thread t owns row t of the [NUM_PASSES * 256] rows; lanes read the row rotated so banks stay distinct
+    for (int row = tid; row < NUM_PASSES * RADIX; row += HIST32_THREADS) {
+        uint32_t sum = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) sum += s_cnt[row * 32 + ((j + tid) & 31)];
+        if (sum) atomicAdd(&ghist[row], (unsigned long long)sum);
+    }
+}
+
 // Same, for inputs whose base pointer is not 16-byte aligned (element-wise loads).
 template <typename ElemT>
 __global__ void __launch_bounds__(HIST_THREADS)
@@ -687,12 +748,28 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         const uint64_t per_block = (uint64_t)HIST_THREADS * HIST_VEC_PER_THREAD * (16 / sizeof(ElemT));
         uint64_t blocks = (n + per_block - 1) / per_block;
         if (((uintptr_t)inout & 15u) == 0) {
-            const uint64_t max_blocks = (uint64_t)dev->num_sms * 3;  // 3 x (512 threads, 64 KiB of counters) per SM, grid-stride beyond that
-            if (blocks > max_blocks) blocks = max_blocks;
-            auto kernel = plan.passes == 4 ? digit_histogram_kernel<ElemT, 4> : plan.passes == 3 ? digit_histogram_kernel<ElemT, 3>
-                        : plan.passes == 2 ? digit_histogram_kernel<ElemT, 2> : digit_histogram_kernel<ElemT, 1>;
-            B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HIST_SMEM_BYTES));
-            kernel<<<(unsigned)blocks, HIST_THREADS, HIST_SMEM_BYTES, dev->stream>>>(inout, n, key_mask, 0x101u, ghist, n_dev);
+            // measured at 2^28 (tools/quick_perf.py): keys, 4 digits 0.190 ms against 0.270 with the packed counters (2 digits:
+            // 0.176 / 0.182); pairs, 4 digits 0.330 / 0.350, 2 digits 0.354 / 0.326.  B200RS_HIST_VARIANT=0|1 forces one.
+            const char* hv = getenv("B200RS_HIST_VARIANT");
+            const int hist_variant = hv ? atoi(hv) : ((sizeof(ElemT) == 4 || plan.passes >= 3) ? 1 : 0);
+            if (hist_variant == 1) {
+                // 32-bit lane-private counters, one 1024-thread CTA per SM (keys: issue-bound with the packed counters)
+                const size_t smem = (size_t)plan.passes * RADIX * 32 * sizeof(uint32_t);
+                const uint64_t per_block32 = (uint64_t)HIST32_THREADS * HIST_VEC_PER_THREAD * (16 / sizeof(ElemT));
+                uint64_t blocks32 = (n + per_block32 - 1) / per_block32;
+                if (blocks32 > (uint64_t)dev->num_sms) blocks32 = (uint64_t)dev->num_sms;
+                auto kernel = plan.passes == 4 ? digit_histogram32_kernel<ElemT, 4> : plan.passes == 3 ? digit_histogram32_kernel<ElemT, 3>
+                            : plan.passes == 2 ? digit_histogram32_kernel<ElemT, 2> : digit_histogram32_kernel<ElemT, 1>;
+                B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kernel<<<(unsigned)blocks32, HIST32_THREADS, smem, dev->stream>>>(inout, n, key_mask, ghist, n_dev);
+            } else {
+                const uint64_t max_blocks = (uint64_t)dev->num_sms * 3;  // 3 x (512 threads, 64 KiB of counters) per SM, grid-stride beyond that
+                if (blocks > max_blocks) blocks = max_blocks;
+                auto kernel = plan.passes == 4 ? digit_histogram_kernel<ElemT, 4> : plan.passes == 3 ? digit_histogram_kernel<ElemT, 3>
+                            : plan.passes == 2 ? digit_histogram_kernel<ElemT, 2> : digit_histogram_kernel<ElemT, 1>;
+                B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HIST_SMEM_BYTES));
+                kernel<<<(unsigned)blocks, HIST_THREADS, HIST_SMEM_BYTES, dev->stream>>>(inout, n, key_mask, 0x101u, ghist, n_dev);
+            }
         } else {
             const uint64_t max_blocks = (uint64_t)dev->num_sms * 4;
             if (blocks > max_blocks) blocks = max_blocks;
