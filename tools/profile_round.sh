@@ -1,3 +1,5 @@
+# tools/profile_round.sh -- what produced profiles/r1c_*: GPU tests, smoke, bench (both arms), the ncu launch list and the ncu --set full
+# captures (reports stay in /tmp on the GPU box: only the raw / source CSV pages are brought back).  Run: gpurun -- bash tools/profile_round.sh
 mkdir -p gpurun_out
 set -x
 (time timeout 1200 python -m pytest tests -m gpu -x -q) 2>&1 | tail -6 > gpurun_out/r1c_pytest_gpu.log
