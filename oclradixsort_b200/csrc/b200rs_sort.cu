@@ -63,6 +63,22 @@ __device__ __forceinline__ void red_add_shared(uint32_t addr, uint32_t v) {
 // =================================================================================================
 // Histogram of every digit in one read of the input.
 // =================================================================================================
+// Tail of the histogram kernels (defined below, next to digit_start_kernel's description): the LAST CTA to finish turns
+// every pass's histogram into digit start offsets and writes the pass control words, which saves the separate one-CTA
+// launch.  All threads of that CTA call it.
+__device__ void digit_start_tail(unsigned long long* ghist, int passes, uint64_t n, uint32_t* ctl);
+__device__ __forceinline__ void fused_digit_start(unsigned long long* ghist, int passes, uint64_t n, uint32_t* done_counter, uint32_t* pass_ctl) {
+    __shared__ uint32_t s_last;
+    __threadfence();  // this CTA's histogram atomics are performed before its arrival is counted
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        digit_start_tail(ghist, passes, n, pass_ctl);  // every 256 threads take one pass at a time (blockDim.x is a multiple of 256)
+    }
+}
+
 constexpr int HIST_THREADS = 512;
 constexpr int HIST_VEC_PER_THREAD = 4;  // uint4 loads in flight per thread
 constexpr int HIST_ROWS = RADIX / 2;    // two 16-bit counters per word: digits r (low half) and r + 128 (high half)
@@ -78,7 +94,8 @@ constexpr size_t HIST_SMEM_BYTES = (size_t)MAX_PASSES * HIST_ROWS * 32 * sizeof(
 template <typename ElemT, int NUM_PASSES>
 __global__ void __launch_bounds__(HIST_THREADS)
 digit_histogram_kernel(const ElemT* __restrict__ in, uint64_t n, uint32_t key_mask, uint32_t mul_0x101 /* 0x101, kept in a register */,
-                       unsigned long long* __restrict__ ghist /*[num_passes][RADIX]*/, const unsigned long long* __restrict__ n_dev) {
+                       unsigned long long* __restrict__ ghist /*[num_passes][RADIX]*/, const unsigned long long* __restrict__ n_dev,
+                       uint32_t* done_counter /* non-null: fused digit starts */, uint32_t* pass_ctl) {
     extern __shared__ __align__(16) uint32_t s_cnt[];  // [MAX_PASSES][HIST_ROWS][32 lanes]
     if (n_dev) n = min(n, (uint64_t)*n_dev);  // element count decided on the device (multi-GPU sort): n is only the upper bound
     const int tid = threadIdx.x, lane = tid & 31;
@@ -151,6 +168,7 @@ digit_histogram_kernel(const ElemT* __restrict__ in, uint64_t n, uint32_t key_ma
         if (i < n) count(Elem<ElemT>::key(in[i]));
     }
     drain();
+    if (done_counter) fused_digit_start(ghist, NUM_PASSES, n, done_counter, pass_ctl);
 }
 
 // Variant with one 32-bit counter per (digit, lane): the 16-bit packing above costs two instructions per digit
@@ -162,7 +180,7 @@ constexpr int HIST32_THREADS = 1024;
 template <typename ElemT, int NUM_PASSES>
 __global__ void __launch_bounds__(HIST32_THREADS, 1)
 digit_histogram32_kernel(const ElemT* __restrict__ in, uint64_t n, uint32_t key_mask, unsigned long long* __restrict__ ghist /*[num_passes][RADIX]*/,
-                         const unsigned long long* __restrict__ n_dev) {
+                         const unsigned long long* __restrict__ n_dev, uint32_t* done_counter /* non-null: fused digit starts */, uint32_t* pass_ctl) {
     extern __shared__ __align__(16) uint32_t s_cnt[];  // [NUM_PASSES][RADIX][32 lanes]
     if (n_dev) n = min(n, (uint64_t)*n_dev);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -212,6 +230,7 @@ digit_histogram32_kernel(const ElemT* __restrict__ in, uint64_t n, uint32_t key_
         for (int j = 0; j < 32; ++j) sum += s_cnt[row * 32 + ((j + tid) & 31)];
         if (sum) atomicAdd(&ghist[row], (unsigned long long)sum);
     }
+    if (done_counter) fused_digit_start(ghist, NUM_PASSES, n, done_counter, pass_ctl);
 }
 
 // Same, for inputs whose base pointer is not 16-byte aligned (element-wise loads).
@@ -342,6 +361,39 @@ __device__ __forceinline__ T block_exclusive_scan_256(T x, T* warp_totals /*[8] 
         if (w < warp) base += warp_totals[w];
     asm volatile("bar.sync 1, 256;" ::: "memory");  // warp_totals may be reused by the caller
     return base + inc - x;
+}
+
+// See fused_digit_start.  Same result as digit_start_kernel (b200rs_onesweep2.cuh): per pass, in-place exclusive scan of the
+// 256-bin histogram and the pass control word (1 = one digit holds every element: the pass only copies).  Group g of 256
+// threads handles passes g, g + groups, ... concurrently (each pass is an L2 round trip plus a scan: done one after the
+// other by 256 threads it took as long as the separate launch it replaces); group g synchronises on named barrier 1 + g.
+__device__ __noinline__ void digit_start_tail(unsigned long long* ghist, int passes, uint64_t n, uint32_t* ctl) {
+    __shared__ uint64_t scratch[MAX_PASSES][RADIX / 32];
+    const int group = threadIdx.x >> 8, groups = blockDim.x >> 8, t = threadIdx.x & 255;
+    const int lane = t & 31, warp = t >> 5;
+    for (int p = group; p < passes; p += groups) {
+        unsigned long long* h = ghist + (size_t)p * RADIX;
+        const uint64_t x = __ldcg(h + t);  // written by other CTAs' atomics: read at L2
+        uint64_t inc = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += y;
+        }
+        const uint32_t degenerate_here = __ballot_sync(0xffffffffu, x == n);
+        if (lane == 31) scratch[group][warp] = inc | (degenerate_here ? 1ull << 63 : 0ull);  // counts are < 2^63: bit 63 carries the flag
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory");
+        uint64_t base = 0, any = 0;
+#pragma unroll
+        for (int w = 0; w < RADIX / 32; ++w) {
+            const uint64_t v = scratch[group][w];
+            any |= v;
+            if (w < warp) base += v & ~(1ull << 63);
+        }
+        h[t] = base + inc - x;
+        if (t == 0) ctl[p] = (uint32_t)(any >> 63);  // PASS_IDENTITY == 1
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory");  // scratch[group] is reused by this group's next pass
+    }
 }
 
 // digit of a key: byte `shift/8` (PRMT) when the pass is a whole byte, shift-and-mask otherwise
@@ -543,6 +595,89 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
 #include "b200rs_onesweep2.cuh"
 #include "b200rs_onesweep3.cuh"
 
+// =================================================================================================
+// Small inputs: the whole sort in ONE launch of ONE CTA.
+// =================================================================================================
+// The multi-kernel chain has a floor of ~55 us (memset + histogram + digit starts + one launch and one look-back chain per
+// digit), which the CPU reference beats below ~16K elements -- and the reference's own unit test sweeps 1K .. 1M
+// (UnitTest/main.cpp:105).  Up to SMALL_CAP elements everything fits one CTA's shared memory: every pass counts, scans and
+// ranks exactly like a scatter-pass tile (warp-striped order, per-warp counters, ballot multisplit: stable) but scatters
+// into a second shared-memory buffer instead of global memory, and nothing needs a histogram, a ticket or a look-back.
+constexpr int SMALL_THREADS = 256;
+constexpr int SMALL_WARPS = SMALL_THREADS / 32;
+constexpr int SMALL_CAP = 8192;  // elements: 2 x 64 KiB of staging for pairs
+template <typename ElemT>
+struct SmallSortSmem {
+    alignas(16) ElemT buf[2][SMALL_CAP];
+    uint32_t warp_offset[SMALL_WARPS][RADIX];
+    uint32_t scan_scratch[RADIX / 32];
+    uint32_t dummy[32];
+};
+
+template <typename ElemT>
+__global__ void __launch_bounds__(SMALL_THREADS, 1)
+small_sort_kernel(ElemT* __restrict__ inout, uint32_t n, int sort_bits, uint32_t minus_one) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmallSortSmem<ElemT>& s = *reinterpret_cast<SmallSortSmem<ElemT>*>(smem_raw);
+    constexpr uint32_t E = (uint32_t)sizeof(ElemT);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t j = tid; j < n; j += SMALL_THREADS) s.buf[0][j] = inout[j];
+    // warp w owns the contiguous slice [w * slice, (w + 1) * slice); element (i, lane) of it is slice_base + 32 i + lane,
+    // so (warp, i, lane) order is input order: the stability argument of the scatter pass
+    const uint32_t ipt = (n + SMALL_THREADS - 1) / SMALL_THREADS;  // <= 32
+    const uint32_t slice_base = (uint32_t)warp * ipt * 32u + (uint32_t)lane;
+    const uint32_t my_offset = smem_addr(&s.warp_offset[warp][0]);
+    const uint32_t le = lanemask_le(), gt = lanemask_gt();
+    const uint32_t dummy = smem_addr(&s.dummy[lane]);
+    int cur = 0;
+    for (int shift = 0; shift < sort_bits; shift += RADIX_BITS) {
+        const int width = sort_bits - shift < RADIX_BITS ? sort_bits - shift : RADIX_BITS;
+        const uint32_t digit_mask = (1u << width) - 1u;
+        for (int i = tid; i < SMALL_WARPS * RADIX; i += SMALL_THREADS) (&s.warp_offset[0][0])[i] = 0;
+        __syncthreads();  // also: the load is complete (first pass)
+        const ElemT* src = s.buf[cur];
+        const uint32_t dst = smem_addr(&s.buf[cur ^ 1][0]);
+        for (uint32_t i = 0; i < ipt; ++i) {
+            const uint32_t j = slice_base + i * 32u;
+            if (j < n) red_add_shared(my_offset + 4u * ((Elem<ElemT>::key(src[j]) >> shift) & digit_mask), 1u);
+        }
+        __syncthreads();
+        {   // one thread per digit: bin starts, then the running slot of every (warp, digit) as a biased byte address
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < SMALL_WARPS; ++w) total += s.warp_offset[w][tid];
+            const uint32_t sbase = block_exclusive_scan_256<uint32_t>(total, s.scan_scratch, tid);
+            uint32_t run = dst + E * sbase - E;
+#pragma unroll
+            for (int w = 0; w < SMALL_WARPS; ++w) {
+                const uint32_t c = s.warp_offset[w][tid];
+                s.warp_offset[w][tid] = run;
+                run += E * c;
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = 0; i < ipt; ++i) {
+            const uint32_t j = slice_base + i * 32u;
+            const bool live = j < n;
+            ElemT e = ElemT();
+            if (live) e = src[j];
+            const uint32_t digit = live ? ((Elem<ElemT>::key(e) >> shift) & digit_mask) : (uint32_t)(RADIX - 1);
+            uint32_t peers = same_digit_lanes<RANK_BALLOT>(digit, minus_one);
+            const uint32_t live_lanes = __ballot_sync(0xffffffffu, live);
+            peers = live ? (peers & live_lanes) : (1u << lane);  // padding lanes are nobody's peers
+            const uint32_t upto = E * (uint32_t)__popc(peers & le);
+            const bool leader = (peers & gt) == 0 && live;
+            uint32_t base = atom_add_shared(leader ? my_offset + 4u * digit : dummy, upto);
+            base = __shfl_sync(0xffffffffu, base, 31 - __clz(peers));
+            if (live) st_shared(base + upto, e);
+        }
+        cur ^= 1;
+        __syncthreads();  // every warp is done with its counter row and the scatter is complete
+    }
+    __syncthreads();  // (covers sort_bits == 0: the load)
+    for (uint32_t j = tid; j < n; j += SMALL_THREADS) inout[j] = s.buf[cur][j];
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 
 // Compiled variants; index chosen by B200RS_KEYS_VARIANT / B200RS_PAIRS_VARIANT (development knob), default 0.
@@ -722,6 +857,19 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     if (n <= 1 || plan.passes == 0) return B200RS_OK;  // nothing to order
 
     b200rs_device_guard guard(dev);
+    if (n <= (uint64_t)SMALL_CAP && !n_dev && !(getenv("B200RS_NO_SMALL_PATH") && atoi(getenv("B200RS_NO_SMALL_PATH")))) {
+        // one launch of one CTA: all passes in shared memory (no histogram, no tickets, no look-back, no temp storage)
+        char small_label[48];
+        snprintf(small_label, sizeof(small_label), "small_sort_%s", what);
+        const size_t smem = sizeof(SmallSortSmem<ElemT>);
+        B200RS_CUDA(cudaFuncSetAttribute(small_sort_kernel<ElemT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            b200rs_launch_scope scope(dev, small_label, n, 2ull * n * sizeof(ElemT));
+            small_sort_kernel<ElemT><<<1, SMALL_THREADS, smem, dev->stream>>>(inout, (uint32_t)n, sort_bits, 0xffffffffu);
+        }
+        B200RS_CUDA(cudaGetLastError());
+        return B200RS_OK;
+    }
     const Variant& var = pick_variant<ElemT>();
     const uint64_t tile_elems = (uint64_t)var.threads * var.ipt;
     const uint32_t num_tiles = (uint32_t)((n + tile_elems - 1) / tile_elems);
@@ -742,6 +890,10 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
 
     const uint32_t key_mask = sort_bits == 32 ? 0xffffffffu : ((1u << sort_bits) - 1u);
     char label[48];
+    uint32_t* pass_ctl = tickets + 32;  // [passes], inside the zeroed ticket block
+    // generation >= 2 kernels need the pre-scanned histograms + pass control words: the aligned histogram kernels do that in
+    // their last CTA (fused_digit_start); only the unaligned fallback still needs the separate digit_start launch
+    uint32_t* done_counter = var.gen >= 2 && ((uintptr_t)inout & 15u) == 0 ? tickets + 48 : nullptr;
     {
         snprintf(label, sizeof(label), "digit_histogram_%s", what);
         b200rs_launch_scope scope(dev, label, n, n * sizeof(ElemT));
@@ -761,14 +913,14 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
                 auto kernel = plan.passes == 4 ? digit_histogram32_kernel<ElemT, 4> : plan.passes == 3 ? digit_histogram32_kernel<ElemT, 3>
                             : plan.passes == 2 ? digit_histogram32_kernel<ElemT, 2> : digit_histogram32_kernel<ElemT, 1>;
                 B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kernel<<<(unsigned)blocks32, HIST32_THREADS, smem, dev->stream>>>(inout, n, key_mask, ghist, n_dev);
+                kernel<<<(unsigned)blocks32, HIST32_THREADS, smem, dev->stream>>>(inout, n, key_mask, ghist, n_dev, done_counter, pass_ctl);
             } else {
                 const uint64_t max_blocks = (uint64_t)dev->num_sms * 3;  // 3 x (512 threads, 64 KiB of counters) per SM, grid-stride beyond that
                 if (blocks > max_blocks) blocks = max_blocks;
                 auto kernel = plan.passes == 4 ? digit_histogram_kernel<ElemT, 4> : plan.passes == 3 ? digit_histogram_kernel<ElemT, 3>
                             : plan.passes == 2 ? digit_histogram_kernel<ElemT, 2> : digit_histogram_kernel<ElemT, 1>;
                 B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HIST_SMEM_BYTES));
-                kernel<<<(unsigned)blocks, HIST_THREADS, HIST_SMEM_BYTES, dev->stream>>>(inout, n, key_mask, 0x101u, ghist, n_dev);
+                kernel<<<(unsigned)blocks, HIST_THREADS, HIST_SMEM_BYTES, dev->stream>>>(inout, n, key_mask, 0x101u, ghist, n_dev, done_counter, pass_ctl);
             }
         } else {
             const uint64_t max_blocks = (uint64_t)dev->num_sms * 4;
@@ -777,8 +929,7 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         }
     }
     B200RS_CUDA(cudaGetLastError());
-    uint32_t* pass_ctl = tickets + 32;  // [passes], inside the zeroed ticket block
-    if (var.gen >= 2) {
+    if (var.gen >= 2 && !done_counter) {
         b200rs_launch_scope scope(dev, "digit_start", (uint64_t)plan.passes * RADIX, (uint64_t)plan.passes * RADIX * 16);
         digit_start_kernel<<<1, RADIX, 0, dev->stream>>>(ghist, plan.passes, n, n_dev, pass_ctl);
     }

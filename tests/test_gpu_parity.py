@@ -98,6 +98,21 @@ def test_sort_keys_partial_bits_stable_on_ignored_bits(ctx, bits):
     assert np.array_equal(_sort_keys(ctx, k, bits), po.sort_u32(k, bits)), bits
 
 
+@pytest.mark.parametrize("n", [2, 33, 1000, 4097, 8191, 8192, 8193])
+def test_small_inputs_single_cta_path(ctx, n):
+    """n <= 8192 takes the one-launch, one-CTA sort (small_sort_kernel); 8193 is the first size of the multi-kernel chain.
+    Partial sortBits (stability on the ignored bits), low-entropy keys (stability of pairs) and every tail shape."""
+    ob = ctx[0]
+    for bits in (32, 20, 8, 3):
+        k = _keys("uniform", n, seed=bits)
+        assert np.array_equal(_sort_keys(ctx, k, bits), po.sort_u32(k, bits)), (n, bits)
+    for kind in ("few", "lowbyte", "allequal", "strided", "and3"):
+        kv = np.empty(n, dtype=ob.PAIR_DTYPE)
+        kv["key"], kv["value"] = _keys(kind, n), np.arange(n, dtype=np.uint32)
+        for bits in (32, 12):
+            assert np.array_equal(_sort_pairs(ctx, kv, bits), po.sort_pairs(kv, bits)), (n, kind, bits)
+
+
 @pytest.mark.parametrize("n", SIZES)
 def test_sort_pairs_sizes_uniform(ctx, n):
     ob = ctx[0]

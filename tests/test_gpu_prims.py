@@ -115,5 +115,5 @@ def test_cpp_dropin_prims_stopwatch_profile_csv(tmp_path):
     r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "PRIMS DROPIN OK" in r.stdout, (r.stdout + r.stderr)[-2000:]
     rows = open(tmp_path / "gpurun_out_profile_test.csv").read().strip().splitlines()
-    assert len(rows) >= 10 and rows[0].startswith('"digit_histogram_keys"'), rows[:3]
+    assert len(rows) >= 8 and rows[0].startswith('"digit_histogram_keys"'), rows[:3]
     assert all(len(r.split(",")) == 5 for r in rows)
