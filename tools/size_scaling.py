@@ -23,3 +23,27 @@ with torch.cuda.stream(st):
             print(f"{what} 2^{log2n}: best scatter pass {best:.4f} ms = {2*n*4*width/best/1e6:.0f} GB/s; hist {prof[0]['ms']:.4f}", flush=True)
             del src, work
     p.release()
+
+# ---- BASELINE config 3: exclusive scan, 1K .. 2^30, full-range inputs (wrap-around), checked against torch.cumsum ----
+with torch.cuda.stream(st):
+    d = ob.DeviceUtils.allocate(ob.TYPE_CL, 0, cuda_stream=st.cuda_stream)
+    p = ob.Pprims()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    print("| scan n | ms | Gelem/s | GB/s (8 B/elem) | total ok | result ok |\n|---|---:|---:|---:|---|---|")
+    for log2n in list(range(10, 31, 2)) + [20.5]:
+        n = (1 << int(log2n)) + (1 if log2n != int(log2n) else 0)  # 20.5 stands for 2^20 + 1 (the reference refuses >= 2^20)
+        s = torch.randint(-2**31, 2**31, (n,), device="cuda", dtype=torch.int32, generator=g)
+        o = torch.empty_like(s)
+        sb, db = ob.Buffer(d, n, np.uint32, ptr=s.data_ptr()), ob.Buffer(d, n, np.uint32, ptr=o.data_ptr())
+        best = 1e9
+        for it in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st); p.scan(d, db, sb, n); e1.record(st); st.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        total = p.scan(d, db, sb, n, sumOut=True)
+        c = torch.cumsum(s.to(torch.int64), 0)
+        want = (c - s).to(torch.int32)
+        ok = bool(torch.equal(o, want)); tok = total == (int(c[-1].item()) & 0xFFFFFFFF)
+        print(f"| {n} | {best:.4f} | {n/best/1e6:.1f} | {n*8/best/1e6:.0f} | {'yes' if tok else 'NO'} | {'yes' if ok else 'NO'} |", flush=True)
+        del s, o, c, want
+    p.release()
