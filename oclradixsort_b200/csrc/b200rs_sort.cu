@@ -747,6 +747,8 @@ template <> struct Variants<uint32_t> {
             B200RS_VARIANT2S(uint32_t, 256, 32, 4),  // 40  staged tile swizzled
             B200RS_VARIANT2S(uint32_t, 256, 35, 4),  // 41
             B200RS_VARIANT2S(uint32_t, 256, 36, 4),  // 42
+            B200RS_VARIANT2(uint32_t, 256, 8, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),    // 43  mid-size inputs (see mid_index)
+            B200RS_VARIANT2(uint32_t, 256, 16, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 44
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
@@ -756,6 +758,7 @@ template <> struct Variants<uint32_t> {
     // run of the staged tile is TILE/256 slots long, and a multiple of 32 words puts all lanes of a scatter store into
     // one shared-memory bank (256x32: 1.30 ms per pass on presorted keys, 256x35: 0.58; uniform keys: 0.66 both)
     static int default_index() { return 38; }
+    static int mid_index() { return 43; }  // 256 x 8 = 2048-key tiles
 };
 template <> struct Variants<uint2> {
     static const Variant* list(int* count) {
@@ -792,22 +795,33 @@ template <> struct Variants<uint2> {
             B200RS_VARIANT2(uint2, 256, 21, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 29  21
             B200RS_VARIANT2S(uint2, 384, 16, 3),  // 30  staged tile swizzled
             B200RS_VARIANT2S(uint2, 320, 20, 3),  // 31
+            B200RS_VARIANT2(uint2, 256, 8, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),    // 32  mid-size inputs (see mid_index)
+            B200RS_VARIANT2(uint2, 256, 16, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 33
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
     }
     static const char* env() { return "B200RS_PAIRS_VARIANT"; }
+    static int mid_index() { return 32; }  // 256 x 8 = 2048-pair tiles
     static int default_index() { return 21; }  // 320 threads x 20 pairs = 25 pairs per digit on average (odd, see the keys note), 3 CTAs/SM
 };
-constexpr uint64_t MIN_TILE = 256 * 21;  // smallest tile among the variants: temp storage is sized for it
+// Below MID_N elements the sort is pure latency: a handful of tiles per pass, every CTA a serial chain of ticket, load,
+// count, rank, look-back and write-out, on a mostly empty GPU (63 us for any n from 16K to 1M keys with the full-size tiles).
+// Small tiles put the same elements on 4 x as many SMs and make each chain 4 x shorter.
+constexpr uint64_t MID_N = 1ull << 19;  // measured: 2048-element tiles win up to 2^19 (44-48 us against 63), tie at 2^20
+constexpr uint64_t MIN_TILE = 256 * 21;     // smallest tile among the variants used above MID_N: temp storage is sized for it
+constexpr uint64_t MIN_TILE_MID = 256 * 8;  // ... and up to MID_N
+inline uint64_t min_tile_for(uint64_t n) { return n <= MID_N ? MIN_TILE_MID : MIN_TILE; }
 
 template <typename ElemT>
-const Variant& pick_variant() {
+const Variant& pick_variant(uint64_t n) {
     int count = 0;
     const Variant* v = Variants<ElemT>::list(&count);
     const char* e = getenv(Variants<ElemT>::env());
-    int idx = e ? atoi(e) : Variants<ElemT>::default_index();
-    if (idx < 0 || idx >= count) idx = Variants<ElemT>::default_index();
+    const int auto_idx = n <= MID_N && !(getenv("B200RS_NO_MID_PATH") && atoi(getenv("B200RS_NO_MID_PATH"))) ? Variants<ElemT>::mid_index() : Variants<ElemT>::default_index();
+    int idx = e ? atoi(e) : auto_idx;
+    if (idx < 0 || idx >= count) idx = auto_idx;
+    if ((uint64_t)v[idx].threads * v[idx].ipt < min_tile_for(n)) idx = auto_idx;  // a forced variant whose tiles are smaller than the plan's
     return v[idx];
 }
 
@@ -820,7 +834,7 @@ struct SortPlan {
 template <typename ElemT>
 int make_plan(uint64_t n, int sort_bits, SortPlan* p) {
     if (sort_bits < 0 || sort_bits > 32) return B200RS_ERR_INVALID_ARGUMENT;
-    const uint64_t tiles = (n + MIN_TILE - 1) / MIN_TILE;
+    const uint64_t tiles = (n + min_tile_for(n) - 1) / min_tile_for(n);
     if (tiles > 0x7fffffffull) return B200RS_ERR_TOO_LARGE;
     p->passes = (sort_bits + RADIX_BITS - 1) / RADIX_BITS;
     size_t off = 0;
@@ -870,7 +884,7 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         B200RS_CUDA(cudaGetLastError());
         return B200RS_OK;
     }
-    const Variant& var = pick_variant<ElemT>();
+    const Variant& var = pick_variant<ElemT>(n);
     const uint64_t tile_elems = (uint64_t)var.threads * var.ipt;
     const uint32_t num_tiles = (uint32_t)((n + tile_elems - 1) / tile_elems);
     char* base = static_cast<char*>(temp);
@@ -903,7 +917,7 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
             // measured at 2^28 (tools/quick_perf.py): keys, 4 digits 0.190 ms against 0.270 with the packed counters (2 digits:
             // 0.176 / 0.182); pairs, 4 digits 0.330 / 0.350, 2 digits 0.354 / 0.326.  B200RS_HIST_VARIANT=0|1 forces one.
             const char* hv = getenv("B200RS_HIST_VARIANT");
-            const int hist_variant = hv ? atoi(hv) : ((sizeof(ElemT) == 4 || plan.passes >= 3) ? 1 : 0);
+            const int hist_variant = hv ? atoi(hv) : ((n > MID_N && (sizeof(ElemT) == 4 || plan.passes >= 3)) ? 1 : 0);  // small n: the 128 KiB table costs more to clear and drain than it saves
             if (hist_variant == 1) {
                 // 32-bit lane-private counters, one 1024-thread CTA per SM (keys: issue-bound with the packed counters)
                 const size_t smem = (size_t)plan.passes * RADIX * 32 * sizeof(uint32_t);
