@@ -87,15 +87,16 @@ def test_sort_keys_sizes_uniform(ctx, n):
 
 @pytest.mark.parametrize("kind", KINDS)
 def test_sort_keys_distributions(ctx, kind):
-    for n in (8192 * 3 + 5, 1 << 18):
+    for n in (8192 * 3 + 5, 1 << 18, (1 << 19) + 8960 * 3 + 1):
         k = _keys(kind, n)
         assert np.array_equal(_sort_keys(ctx, k), po.sort_u32(k)), (kind, n)
 
 
 @pytest.mark.parametrize("bits", [0, 1, 4, 8, 12, 16, 20, 24, 28, 31, 32])
 def test_sort_keys_partial_bits_stable_on_ignored_bits(ctx, bits):
-    k = _keys("uniform", 300007)
-    assert np.array_equal(_sort_keys(ctx, k, bits), po.sort_u32(k, bits)), bits
+    for n in (300007, 700001):  # 2048-element tiles / full-size tiles
+        k = _keys("uniform", n)
+        assert np.array_equal(_sort_keys(ctx, k, bits), po.sort_u32(k, bits)), (n, bits)
 
 
 @pytest.mark.parametrize("n", [2, 33, 1000, 4097, 8191, 8192, 8193])
@@ -124,26 +125,29 @@ def test_sort_pairs_sizes_uniform(ctx, n):
 @pytest.mark.parametrize("kind", KINDS)
 def test_sort_pairs_stability(ctx, kind):
     ob = ctx[0]
-    for n in (4096 * 3 + 5, 1 << 18):
+    for n in (4096 * 3 + 5, 1 << 18, (1 << 19) + 6400 * 3 + 1):
         kv = np.empty(n, dtype=ob.PAIR_DTYPE)
         kv["key"], kv["value"] = _keys(kind, n), np.arange(n, dtype=np.uint32)
         got = _sort_pairs(ctx, kv)
         assert np.array_equal(got, po.sort_pairs(kv)), (kind, n)
 
 
-# The scatter pass groups tiles by 8 for its two-level look-back (csrc/b200rs_onesweep2.cuh, LB_GROUP); tiles are
-# 8960 keys / 6400 pairs (8192 / 6144 / 10240 in earlier defaults, still selectable).  Sizes around whole groups, one
-# tile more, one element less, and several groups deep.
+# The scatter pass groups tiles by 8 for its two-level look-back (csrc/b200rs_onesweep2.cuh, LB_GROUP).  Tiles are 2048
+# elements up to 2^19 elements (mid-size path) and 8960 keys / 6400 pairs above.  Sizes around whole groups, one tile
+# more, one element less, and several groups deep -- for both tile sizes.
 GROUP_EDGE_TILES = [7, 8, 9, 16, 17, 41]
 
 
 @pytest.mark.parametrize("tiles", GROUP_EDGE_TILES)
 def test_sort_lookback_group_boundaries(ctx, tiles):
     ob = ctx[0]
-    for n in (tiles * 8960 - 1, tiles * 8960, tiles * 8960 + 1, tiles * 8192 - 1, tiles * 8192, tiles * 8192 + 1, tiles * 10240 + 1):
+    big = 56  # 56 tiles of either default size are more than 2^19 elements: the full-size tiles are in use from there on
+    key_sizes = [tiles * 2048 + d for d in (-1, 0, 1)] + [(big + tiles) * 8960 + d for d in (-1, 0, 1)]
+    pair_sizes = [tiles * 2048 + d for d in (-1, 0, 1)] + [(big + 32 + tiles) * 6400 + d for d in (-1, 0, 1)]
+    for n in key_sizes:
         k = _keys("and3", n)  # low entropy: long equal-key runs cross tile and group edges
         assert np.array_equal(_sort_keys(ctx, k), po.sort_u32(k)), n
-    for n in (tiles * 6400 - 1, tiles * 6400, tiles * 6400 + 1, tiles * 6144 - 1, tiles * 6144, tiles * 6144 + 1):
+    for n in pair_sizes:
         kv = np.empty(n, dtype=ob.PAIR_DTYPE)
         kv["key"], kv["value"] = _keys("few", n), np.arange(n, dtype=np.uint32)
         assert np.array_equal(_sort_pairs(ctx, kv), po.sort_pairs(kv)), n
@@ -154,23 +158,23 @@ def test_sort_skipped_passes(ctx, mask):
     """A pass whose digit is the same for every element moves nothing: the device detects it (digit_start_kernel) and
     that pass's kernel only copies its tiles; 0, 1, 2, 3 or 4 real passes then run."""
     ob = ctx[0]
-    n = 150001
-    k = (_keys("uniform", n) & np.uint32(mask)) | np.uint32(0x5A5A5A5A & ~mask)
-    assert np.array_equal(_sort_keys(ctx, k), po.sort_u32(k)), hex(mask)
-    for bits in (16, 24):
-        assert np.array_equal(_sort_keys(ctx, k, bits), po.sort_u32(k, bits)), (hex(mask), bits)
-    kv = np.empty(n, dtype=ob.PAIR_DTYPE)
-    kv["key"], kv["value"] = k, np.arange(n, dtype=np.uint32)[::-1]
-    assert np.array_equal(_sort_pairs(ctx, kv), po.sort_pairs(kv)), hex(mask)
+    for n in (150001, 650001):  # 2048-element tiles / full-size tiles (identity passes copy whole tiles of either size)
+        k = (_keys("uniform", n) & np.uint32(mask)) | np.uint32(0x5A5A5A5A & ~mask)
+        assert np.array_equal(_sort_keys(ctx, k), po.sort_u32(k)), (n, hex(mask))
+        for bits in (16, 24):
+            assert np.array_equal(_sort_keys(ctx, k, bits), po.sort_u32(k, bits)), (n, hex(mask), bits)
+        kv = np.empty(n, dtype=ob.PAIR_DTYPE)
+        kv["key"], kv["value"] = k, np.arange(n, dtype=np.uint32)[::-1]
+        assert np.array_equal(_sort_pairs(ctx, kv), po.sort_pairs(kv)), (n, hex(mask))
 
 
 @pytest.mark.parametrize("bits", [4, 12, 16, 24])
 def test_sort_pairs_partial_bits(ctx, bits):
     ob = ctx[0]
-    n = 200003
-    kv = np.empty(n, dtype=ob.PAIR_DTYPE)
-    kv["key"], kv["value"] = _keys("uniform", n), np.arange(n, dtype=np.uint32)[::-1]
-    assert np.array_equal(_sort_pairs(ctx, kv, bits), po.sort_pairs(kv, bits))
+    for n in (200003, 600011):  # 2048-element tiles / full-size tiles
+        kv = np.empty(n, dtype=ob.PAIR_DTYPE)
+        kv["key"], kv["value"] = _keys("uniform", n), np.arange(n, dtype=np.uint32)[::-1]
+        assert np.array_equal(_sort_pairs(ctx, kv, bits), po.sort_pairs(kv, bits)), (n, bits)
 
 
 def test_reference_unit_test_vectors(ctx, golden_dir):
