@@ -47,7 +47,8 @@ struct BufferBase {
     enum BufferType {
         BUFFER,
         BUFFER_CONST, BUFFER_STAGING, BUFFER_APPEND, BUFFER_RAW, BUFFER_W_COUNTER, BUFFER_INDEX, BUFFER_VERTEX,  // DX11 kinds, unused
-        BUFFER_ZERO_COPY,
+        BUFFER_ZERO_COPY,  // accepted and allocated like BUFFER: the CL backend's CL_MEM_ALLOC_HOST_PTR (AdlCL.inl:381-382) would be host memory
+                           // behind PCIe here, i.e. a sort at ~50 GB/s; getHostPtr / returnHostPtr go through the pinned staging block instead
     };
 };
 
