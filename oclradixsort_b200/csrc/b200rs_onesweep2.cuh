@@ -24,7 +24,8 @@
 enum WriteOut { WO_ELEM = 0, WO_BULK = 1 };
 enum LookbackOrder { ORDER_LATE = 0, ORDER_EARLY = 1 };
 enum TileLoad { LOAD_LDG = 0, LOAD_BULK = 1 };
-constexpr uint32_t PASS_IDENTITY = 1u;  // pass control word, see digit_start_kernel  // LOAD_BULK: one cp.async.bulk (TMA) brings the whole tile into shared memory
+constexpr uint32_t PASS_IDENTITY = 1u;  // pass control word, see digit_start_kernel
+constexpr uint32_t PASS_REGULAR = 2u;   // every non-empty digit bin of the pass holds the same count (+-): see SWZ / DSWZ below  // LOAD_BULK: one cp.async.bulk (TMA) brings the whole tile into shared memory
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
     uint32_t v;
@@ -189,6 +190,10 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
     constexpr bool SWIZZLE = SWZ != 0 && WO == WO_ELEM;
     constexpr uint32_t SWZ_MASK = E == 4 ? 0x7cu : 0x78u;  // address bits that select the element inside its 128-byte row
     auto swz = [&](uint32_t a) { return SWIZZLE ? a ^ ((((a >> 7) * 0x9E3779B1u) >> 25) & SWZ_MASK) : a; };
+    // ... and the counter rows are indexed by d ^ (d >> 5) (a bijection on 0..255): digits that are multiples of 16 or 32 --
+    // all a pass over strided keys may contain -- would otherwise share two banks or one
+    auto cswz = [&](uint32_t d) { return SWIZZLE ? d ^ (d >> 5) : d; };
+    const uint32_t ctid = cswz((uint32_t)tid);  // digit threads: where digit tid's counter lives in a row
 
     // ---- 1. warp-striped load + per-warp digit counts ----
     ElemT elem[IPT];
@@ -207,7 +212,7 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
     for (int i = 0; i < IPT; ++i)
         if (FULL || slice + i * 32 < valid) {
             const uint32_t d = digit_of_opaque<BYTE_DIGIT>(Elem<ElemT>::key(elem[i]), shift, digit_mask, prmt_sel);
-            red_add_shared(my_offset + 4u * d, 1u);
+            red_add_shared(my_offset + 4u * cswz(d), 1u);
         }
     __syncthreads();
 
@@ -216,7 +221,7 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
     uint64_t exclusive = 0;                    // digit threads: global index of the first one
     if (tid < RADIX) {
 #pragma unroll
-        for (int w = 0; w < Cfg::WARPS; ++w) total += s.warp_offset[w][tid];
+        for (int w = 0; w < Cfg::WARPS; ++w) total += s.warp_offset[w][ctid];
         mates = lookback3_publish(lb, tile, pass, total, tid);
         uint32_t a = 0, region = total;
         if (ORDER == ORDER_EARLY) {
@@ -232,8 +237,8 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
         uint32_t run = staged + E * sbase - E;
 #pragma unroll
         for (int w = 0; w < Cfg::WARPS; ++w) {
-            const uint32_t c = s.warp_offset[w][tid];
-            s.warp_offset[w][tid] = run;
+            const uint32_t c = s.warp_offset[w][ctid];
+            s.warp_offset[w][ctid] = run;
             run += E * c;
         }
     }
@@ -256,7 +261,7 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
         // no branch.  My slot's address = (claimed base) + upto, thanks to the -E bias of the counters.
         const uint32_t upto = E * (uint32_t)__popc(peers & le);
         const bool leader = (peers & gt) == 0 && live;
-        uint32_t base = atom_add_shared(leader ? my_offset + 4u * digit : dummy, upto);
+        uint32_t base = atom_add_shared(leader ? my_offset + 4u * cswz(digit) : dummy, upto);
         base = __shfl_sync(0xffffffffu, base, 31 - __clz(peers));
         if (live) st_shared(swz(base + upto), elem[i]);
     }
@@ -313,7 +318,10 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
     }
 }
 
-template <typename ElemT, int THREADS, int IPT, int MIN_CTAS, int WO, int ORDER, int LOAD, int SWZ = 0>
+// DSWZ: the swizzled body is compiled in next to the plain one and taken (CTA-uniform branch, like the identity-pass test)
+// only in passes that digit_start flagged PASS_REGULAR -- presorted / reversed / strided keys, or a shuffled permutation of
+// a full range -- so inputs with ordinary histograms never pay for the swizzle's 7 + 4 extra instructions per element.
+template <typename ElemT, int THREADS, int IPT, int MIN_CTAS, int WO, int ORDER, int LOAD, int SWZ = 0, int DSWZ = 0>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t n, int shift, uint32_t digit_mask,
                  const unsigned long long* __restrict__ digit_start /*[RADIX]: exclusive scan of the pass's histogram*/, Lookback3 lb,
@@ -377,12 +385,39 @@ onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t
     const bool byte_digit = digit_mask == (uint32_t)(RADIX - 1);
     const uint32_t prmt_sel = 0x4440u | (uint32_t)(shift >> 3);
 
-    if (valid == Cfg::TILE) {
+    if (DSWZ && valid == Cfg::TILE && byte_digit && (s.ctl & PASS_REGULAR)) {
+        onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, true, true, 1>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, in_aligned);
+    } else if (valid == Cfg::TILE) {
         if (byte_digit) onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, true, true, SWZ>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, in_aligned);
         else            onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, true, false, SWZ>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, in_aligned);
     } else {
         onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, false, false, SWZ>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, false);
     }
+}
+
+// PASS_REGULAR test for one 256-bin histogram (x = this thread's bin), 256 threads, block-wide barriers: between 2 and 255
+// non-empty bins whose counts differ by at most 1.  Random keys practically never pass it (two bins of 2^27 random keys
+// differ by ~16 000; a looser bound of max >> 12 let "two distinct values" through and cost it 17 %); a pass over strided
+// keys that uses only every 16th or 32nd digit does.  With all 256 bins equally full the odd tile shapes are already conflict-free and the plain body is
+// faster (presorted keys 0.576 against 0.674 ms), so that case is left alone.
+__device__ __forceinline__ uint32_t bins_are_regular(uint64_t x, int tid) {
+    __shared__ uint64_t s_min[RADIX / 32], s_max[RADIX / 32];
+    __shared__ uint32_t s_cnt[RADIX / 32];
+    uint64_t mn = x ? x : ~0ull, mx = x;
+    uint32_t cnt = x ? 1u : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    }
+    if ((tid & 31) == 0) { s_min[tid >> 5] = mn; s_max[tid >> 5] = mx; s_cnt[tid >> 5] = cnt; }
+    __syncthreads();
+    mn = ~0ull; mx = 0; cnt = 0;
+#pragma unroll
+    for (int w = 0; w < RADIX / 32; ++w) { mn = min(mn, s_min[w]); mx = max(mx, s_max[w]); cnt += s_cnt[w]; }
+    __syncthreads();
+    return cnt >= 2u && cnt < (uint32_t)RADIX && mx - mn <= 1ull ? 1u : 0u;
 }
 
 // One CTA, after the histogram kernel.  For each pass: in-place exclusive scan of its 256-bin histogram
@@ -396,7 +431,8 @@ __global__ void __launch_bounds__(RADIX) digit_start_kernel(unsigned long long* 
         unsigned long long* h = ghist + (size_t)p * RADIX;
         const uint64_t x = h[threadIdx.x];
         const int degenerate = __syncthreads_or(x == n);
+        const uint32_t regular = bins_are_regular(x, threadIdx.x);  // (block-wide, uses __syncthreads)
         h[threadIdx.x] = block_exclusive_scan_256<uint64_t>(x, scratch, threadIdx.x);
-        if (threadIdx.x == 0) ctl[p] = degenerate ? PASS_IDENTITY : 0u;
+        if (threadIdx.x == 0) ctl[p] = (degenerate ? PASS_IDENTITY : 0u) | (regular ? PASS_REGULAR : 0u);
     }
 }

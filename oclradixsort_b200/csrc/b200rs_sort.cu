@@ -368,7 +368,8 @@ __device__ __forceinline__ T block_exclusive_scan_256(T x, T* warp_totals /*[8] 
 // threads handles passes g, g + groups, ... concurrently (each pass is an L2 round trip plus a scan: done one after the
 // other by 256 threads it took as long as the separate launch it replaces); group g synchronises on named barrier 1 + g.
 __device__ __noinline__ void digit_start_tail(unsigned long long* ghist, int passes, uint64_t n, uint32_t* ctl) {
-    __shared__ uint64_t scratch[MAX_PASSES][RADIX / 32];
+    __shared__ uint64_t scratch[MAX_PASSES][RADIX / 32], s_min[MAX_PASSES][RADIX / 32], s_max[MAX_PASSES][RADIX / 32];
+    __shared__ uint32_t s_cnt[MAX_PASSES][RADIX / 32];
     const int group = threadIdx.x >> 8, groups = blockDim.x >> 8, t = threadIdx.x & 255;
     const int lane = t & 31, warp = t >> 5;
     for (int p = group; p < passes; p += groups) {
@@ -381,17 +382,32 @@ __device__ __noinline__ void digit_start_tail(unsigned long long* ghist, int pas
             if (lane >= d) inc += y;
         }
         const uint32_t degenerate_here = __ballot_sync(0xffffffffu, x == n);
-        if (lane == 31) scratch[group][warp] = inc | (degenerate_here ? 1ull << 63 : 0ull);  // counts are < 2^63: bit 63 carries the flag
+        // PASS_REGULAR (see bins_are_regular in b200rs_onesweep2.cuh): min / max / number of the non-empty bins
+        uint64_t mn = x ? x : ~0ull, mx = x;
+        uint32_t cnt = x ? 1u : 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        }
+        if (lane == 31) {
+            scratch[group][warp] = inc | (degenerate_here ? 1ull << 63 : 0ull);  // counts are < 2^63: bit 63 carries the flag
+            s_min[group][warp] = mn; s_max[group][warp] = mx; s_cnt[group][warp] = cnt;
+        }
         asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory");
         uint64_t base = 0, any = 0;
+        mn = ~0ull; mx = 0; cnt = 0;
 #pragma unroll
         for (int w = 0; w < RADIX / 32; ++w) {
             const uint64_t v = scratch[group][w];
             any |= v;
             if (w < warp) base += v & ~(1ull << 63);
+            mn = min(mn, s_min[group][w]); mx = max(mx, s_max[group][w]); cnt += s_cnt[group][w];
         }
         h[t] = base + inc - x;
-        if (t == 0) ctl[p] = (uint32_t)(any >> 63);  // PASS_IDENTITY == 1
+        const uint32_t regular = cnt >= 2u && cnt < (uint32_t)RADIX && mx - mn <= 1ull ? 2u : 0u;  // PASS_REGULAR == 2
+        if (t == 0) ctl[p] = (uint32_t)(any >> 63) | regular;  // PASS_IDENTITY == 1
         asm volatile("bar.sync %0, 256;" ::"r"(1 + group) : "memory");  // scratch[group] is reused by this group's next pass
     }
 }
@@ -695,6 +711,8 @@ struct Variant {
     Variant{(const void*)onesweep_kernel<ElemT, THREADS, IPT, MODE, MIN_CTAS, false, false, W>, THREADS, IPT, sizeof(typename OnesweepConfig<ElemT, THREADS, IPT>::Smem), #THREADS "x" #IPT ":" #MODE "/" #MIN_CTAS "w" #W, 1, 0}
 #define B200RS_VARIANT2(ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER, LOAD) \
     Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER, LOAD>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":" #WO ":" #ORDER ":" #LOAD, 2, 0}
+#define B200RS_VARIANT2D(ElemT, THREADS, IPT, MIN_CTAS) \
+    Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO_ELEM, ORDER_LATE, LOAD_LDG, 0, 1>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO_ELEM>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":swizzled-when-regular", 2, 0}
 #define B200RS_VARIANT2S(ElemT, THREADS, IPT, MIN_CTAS) \
     Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO_ELEM, ORDER_LATE, LOAD_LDG, 1>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO_ELEM>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":swizzled", 2, 0}
 #define B200RS_VARIANT3(ElemT, THREADS, IPT, MIN_CTAS, PF) \
@@ -749,6 +767,7 @@ template <> struct Variants<uint32_t> {
             B200RS_VARIANT2S(uint32_t, 256, 36, 4),  // 42
             B200RS_VARIANT2(uint32_t, 256, 8, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),    // 43  mid-size inputs (see mid_index)
             B200RS_VARIANT2(uint32_t, 256, 16, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 44
+            B200RS_VARIANT2D(uint32_t, 256, 35, 4),  // 45  swizzled body in passes flagged PASS_REGULAR
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
@@ -757,7 +776,7 @@ template <> struct Variants<uint32_t> {
     // 256 threads x 35 keys, 4 CTAs/SM.  35 and not 32: with evenly spread digits (presorted / reversed / strided keys) every
     // run of the staged tile is TILE/256 slots long, and a multiple of 32 words puts all lanes of a scatter store into
     // one shared-memory bank (256x32: 1.30 ms per pass on presorted keys, 256x35: 0.58; uniform keys: 0.66 both)
-    static int default_index() { return 38; }
+    static int default_index() { return 45; }  // = 38 (256 x 35) plus the swizzled body for passes flagged PASS_REGULAR
     static int mid_index() { return 43; }  // 256 x 8 = 2048-key tiles
 };
 template <> struct Variants<uint2> {
@@ -797,6 +816,7 @@ template <> struct Variants<uint2> {
             B200RS_VARIANT2S(uint2, 320, 20, 3),  // 31
             B200RS_VARIANT2(uint2, 256, 8, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),    // 32  mid-size inputs (see mid_index)
             B200RS_VARIANT2(uint2, 256, 16, 4, WO_ELEM, ORDER_LATE, LOAD_LDG),   // 33
+            B200RS_VARIANT2D(uint2, 320, 20, 3),  // 34  swizzled body in passes flagged PASS_REGULAR
         };
         *count = sizeof(v) / sizeof(v[0]);
         return v;
