@@ -57,3 +57,22 @@ def test_product_never_imports_oracle():
                     if "pyoracle" in text or "radixsort_oracle" in text or "liboracle" in text:
                         bad.append(os.path.join(dirpath, fn))
     assert not bad, bad
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/b200rs.h must compile as C99 on its own (what a cgo / JNI / ctypes-cffi binding sees)."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "b200rs.h"\nint main(void) { b200rs_pair p = {1u, 2u}; b200rs_profile_entry e; (void)e; return (int)(p.key + p.value) - 3 + (B200RS_OK); }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_dropin_headers_compile_as_cxx11(tmp_path):
+    """include/Adl + include/Tahoe are what a C++ user of the reference includes: a TU that only includes them must compile
+    with the reference's language level (premake4.lua builds with the compiler default of its day; -std=c++11 here)."""
+    src = tmp_path / "t.cpp"
+    src.write_text('#include <Adl/Adl.h>\n#include <Tahoe/ParallelPrimitives/Pprims.h>\n#include <Tahoe/Algorithm/Sort/RadixSort.h>\n'
+                   'char adl::s_cacheDirectory[128];\nint main() { adl::Stopwatch sw; Tahoe::SortData d(1u, 2u); return (int)d.m_key - 1 + sw.getNIntervals() + 1; }\n')
+    r = subprocess.run(["g++", "-std=c++11", "-Wall", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
