@@ -7,7 +7,10 @@ NVCC   ?= /usr/local/cuda/bin/nvcc
 CXX    ?= g++
 REF    ?= /root/reference
 ARCH   := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v -Iinclude
+# make EXPERIMENTS=1: also compiles the measurement-only kernel variants and the B200RS_* environment knobs (tools/sweep.py);
+# the default (production) library contains neither.
+EXPFLAGS := $(if $(EXPERIMENTS),-DB200RS_EXPERIMENTS,)
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v -Iinclude $(EXPFLAGS)
 CSRC   := oclradixsort_b200/csrc
 SRCS   := $(CSRC)/b200rs_device.cu $(CSRC)/b200rs_scan.cu $(CSRC)/b200rs_sort.cu $(CSRC)/b200rs_host.cu $(CSRC)/b200rs_prims.cu
 OBJS   := $(SRCS:.cu=.o)

@@ -41,6 +41,11 @@ struct b200rs_device {
 
     bool profiling = false;
     std::vector<b200rs_profile_span> spans;
+
+    // kernels whose dynamic shared-memory limit has been raised on this device, with their cached occupancy
+    // (cudaFuncSetAttribute / cudaOccupancyMaxActiveBlocksPerMultiprocessor are paid once per handle, not per call)
+    struct kernel_setup { const void* func; int smem; int threads; int ctas_per_sm; };
+    std::vector<kernel_setup> kernel_setups;
 };
 
 #define B200RS_CUDA(expr)                                   \
@@ -96,6 +101,36 @@ struct b200rs_launch_scope {
         dev->spans.push_back(span);
     }
 };
+
+// Raises `func`'s dynamic shared-memory limit to `smem` bytes the first time the handle sees it; optionally returns the
+// number of co-resident CTAs per SM (cached).  Called before every launch that needs more than 48 KiB.
+static inline int b200rs_kernel_setup(b200rs_device* dev, const void* func, size_t smem, int threads = 0, int* ctas_per_sm = nullptr) {
+    for (auto& k : dev->kernel_setups)
+        if (k.func == func && k.smem == (int)smem && (!ctas_per_sm || k.threads == threads)) {
+            if (ctas_per_sm) *ctas_per_sm = k.ctas_per_sm;
+            return B200RS_OK;
+        }
+    if (smem > 48 * 1024) B200RS_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    if (ctas_per_sm) {
+        B200RS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, threads, smem));
+        *ctas_per_sm = per_sm;
+    }
+    dev->kernel_setups.push_back({func, (int)smem, ctas_per_sm ? threads : 0, per_sm});
+    return B200RS_OK;
+}
+
+// Development knobs (environment variables) exist only in builds made with -DB200RS_EXPERIMENTS (make EXPERIMENTS=1, used
+// by tools/sweep.py); the production library reads no environment variable, so nothing outside the call can change a result.
+static inline int b200rs_exp_env(const char* name, int fallback) {
+#ifdef B200RS_EXPERIMENTS
+    const char* e = getenv(name);
+    return e ? atoi(e) : fallback;
+#else
+    (void)name;
+    return fallback;
+#endif
+}
 
 static inline size_t b200rs_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

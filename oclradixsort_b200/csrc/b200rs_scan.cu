@@ -518,6 +518,11 @@ struct ScanVariant {
 #define B200RS_SCAN_PERSISTENT(T, R) ScanVariant{scan_persistent_kernel<T, R, true>, scan_persistent_kernel<T, R, false>, T, T * R * 4, true, 0}
 #define B200RS_SCAN_RING(T, R, S) ScanVariant{scan_ring_kernel<T, R, S>, scan_lookback_kernel<T, R, false>, T, T * R * 4, true, (size_t)S * T * R * 16}
 const ScanVariant& pick_scan_variant(uint64_t n, int num_sms) {
+    // production: the TMA ring kernel with 96 KiB tiles (one persistent CTA per SM); inputs too small to give every SM a
+    // couple of those use 32 KiB tiles (three CTAs per SM).  The other shapes are compiled only with -DB200RS_EXPERIMENTS.
+    static const ScanVariant big = B200RS_SCAN_RING(512, 12, 2), small = B200RS_SCAN_RING(256, 8, 2);
+    const ScanVariant& production = n >= (uint64_t)num_sms * 2 * 24576 ? big : small;
+#ifdef B200RS_EXPERIMENTS
     static const ScanVariant v[] = {
         B200RS_SCAN_VARIANT(512, 8),  // default: 16384 elements per tile
         B200RS_SCAN_VARIANT(256, 8),
@@ -547,13 +552,12 @@ const ScanVariant& pick_scan_variant(uint64_t n, int num_sms) {
         B200RS_SCAN_RING(1024, 6, 2),     // 25: 96 KiB tiles
         B200RS_SCAN_RING(768, 8, 2),      // 26: 96 KiB tiles
     };
-    // default: the TMA ring kernel with 96 KiB tiles (one persistent CTA per SM); inputs too small to give every SM a
-    // couple of those use 32 KiB tiles (three CTAs per SM)
-    const int auto_idx = n >= (uint64_t)num_sms * 2 * 24576 ? 24 : 20;
-    const char* e = getenv("B200RS_SCAN_VARIANT");
-    int idx = e ? atoi(e) : auto_idx;
-    if (idx < 0 || idx >= (int)(sizeof(v) / sizeof(v[0]))) idx = auto_idx;
-    return v[idx];
+    if (const char* e = getenv("B200RS_SCAN_VARIANT")) {
+        const int idx = atoi(e);
+        if (idx >= 0 && idx < (int)(sizeof(v) / sizeof(v[0]))) return v[idx];
+    }
+#endif
+    return production;
 }
 
 }  // namespace
@@ -589,10 +593,9 @@ extern "C" int b200rs_exclusive_scan_u32(b200rs_device* dev, uint32_t* dst, cons
         auto kernel = vec16 ? var.aligned : var.unaligned;
         uint32_t grid = num_tiles;
         const size_t dyn_smem = vec16 ? var.ring_bytes : 0;
-        if (dyn_smem) B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        int per_sm = 0;
+        B200RS_TRY(b200rs_kernel_setup(dev, (const void*)kernel, dyn_smem, var.threads, &per_sm));
         if (var.persistent && (vec16 || var.ring_bytes == 0)) {
-            int per_sm = 0;
-            B200RS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, var.threads, dyn_smem));
             const uint64_t resident = (uint64_t)(per_sm > 0 ? per_sm : 1) * dev->num_sms;  // every CTA must be resident: tiles spin on lower ones
             if (grid > resident) grid = (uint32_t)resident;
         }

@@ -609,7 +609,9 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
 }
 
 #include "b200rs_onesweep2.cuh"
+#ifdef B200RS_EXPERIMENTS
 #include "b200rs_onesweep3.cuh"
+#endif
 
 // =================================================================================================
 // Small inputs: the whole sort in ONE launch of ONE CTA.
@@ -696,7 +698,11 @@ small_sort_kernel(ElemT* __restrict__ inout, uint32_t n, int sort_bits, uint32_t
 
 // ---- host side -------------------------------------------------------------------------------------
 
-// Compiled variants; index chosen by B200RS_KEYS_VARIANT / B200RS_PAIRS_VARIANT (development knob), default 0.
+// Scatter-pass kernels.  The production library contains exactly two per element type: the full-size tile and the 2048-element
+// tile of the mid-size path.  Every other shape, the generation-1 / generation-3 bodies, the bulk (TMA) load and write-out
+// variants and the measurement-only ranking modes (RANK_MATCH, RANK_ATOMIC_UNORDERED -- the latter is NOT stable by contract)
+// are compiled only with -DB200RS_EXPERIMENTS (make EXPERIMENTS=1), where B200RS_KEYS_VARIANT / B200RS_PAIRS_VARIANT select
+// them by index for tools/sweep.py.
 struct Variant {
     const void* kernel;
     int threads, ipt;
@@ -720,6 +726,13 @@ struct Variant {
 
 template <typename ElemT> struct Variants;
 template <> struct Variants<uint32_t> {
+    // 256 threads x 35 keys, 4 CTAs/SM.  35 and not 32: with evenly spread digits (presorted / reversed / strided keys) every
+    // run of the staged tile is TILE/256 slots long, and a multiple of 32 words puts all lanes of a scatter store into
+    // one shared-memory bank (256x32: 1.30 ms per pass on presorted keys, 256x35: 0.58; uniform keys: 0.66 both); plus the
+    // swizzled body for passes flagged PASS_REGULAR
+    static const Variant& full_size() { static const Variant v = B200RS_VARIANT2D(uint32_t, 256, 35, 4); return v; }
+    static const Variant& mid_size() { static const Variant v = B200RS_VARIANT2(uint32_t, 256, 8, 4, WO_ELEM, ORDER_LATE, LOAD_LDG); return v; }  // 2048-key tiles
+#ifdef B200RS_EXPERIMENTS
     static const Variant* list(int* count) {
         static const Variant v[] = {
             B200RS_VARIANT(uint32_t, 512, 24, RANK_BALLOT, 3),  // default
@@ -773,13 +786,13 @@ template <> struct Variants<uint32_t> {
         return v;
     }
     static const char* env() { return "B200RS_KEYS_VARIANT"; }
-    // 256 threads x 35 keys, 4 CTAs/SM.  35 and not 32: with evenly spread digits (presorted / reversed / strided keys) every
-    // run of the staged tile is TILE/256 slots long, and a multiple of 32 words puts all lanes of a scatter store into
-    // one shared-memory bank (256x32: 1.30 ms per pass on presorted keys, 256x35: 0.58; uniform keys: 0.66 both)
-    static int default_index() { return 45; }  // = 38 (256 x 35) plus the swizzled body for passes flagged PASS_REGULAR
-    static int mid_index() { return 43; }  // 256 x 8 = 2048-key tiles
+#endif
 };
 template <> struct Variants<uint2> {
+    // 320 threads x 20 pairs = 25 pairs per digit on average (odd, see the keys note), 3 CTAs/SM
+    static const Variant& full_size() { static const Variant v = B200RS_VARIANT2(uint2, 320, 20, 3, WO_ELEM, ORDER_LATE, LOAD_LDG); return v; }
+    static const Variant& mid_size() { static const Variant v = B200RS_VARIANT2(uint2, 256, 8, 4, WO_ELEM, ORDER_LATE, LOAD_LDG); return v; }  // 2048-pair tiles
+#ifdef B200RS_EXPERIMENTS
     static const Variant* list(int* count) {
         static const Variant v[] = {
             B200RS_VARIANT(uint2, 384, 16, RANK_BALLOT, 3),  // default
@@ -822,8 +835,7 @@ template <> struct Variants<uint2> {
         return v;
     }
     static const char* env() { return "B200RS_PAIRS_VARIANT"; }
-    static int mid_index() { return 32; }  // 256 x 8 = 2048-pair tiles
-    static int default_index() { return 21; }  // 320 threads x 20 pairs = 25 pairs per digit on average (odd, see the keys note), 3 CTAs/SM
+#endif
 };
 // Below MID_N elements the sort is pure latency: a handful of tiles per pass, every CTA a serial chain of ticket, load,
 // count, rank, look-back and write-out, on a mostly empty GPU (63 us for any n from 16K to 1M keys with the full-size tiles).
@@ -835,14 +847,18 @@ inline uint64_t min_tile_for(uint64_t n) { return n <= MID_N ? MIN_TILE_MID : MI
 
 template <typename ElemT>
 const Variant& pick_variant(uint64_t n) {
-    int count = 0;
-    const Variant* v = Variants<ElemT>::list(&count);
-    const char* e = getenv(Variants<ElemT>::env());
-    const int auto_idx = n <= MID_N && !(getenv("B200RS_NO_MID_PATH") && atoi(getenv("B200RS_NO_MID_PATH"))) ? Variants<ElemT>::mid_index() : Variants<ElemT>::default_index();
-    int idx = e ? atoi(e) : auto_idx;
-    if (idx < 0 || idx >= count) idx = auto_idx;
-    if ((uint64_t)v[idx].threads * v[idx].ipt < min_tile_for(n)) idx = auto_idx;  // a forced variant whose tiles are smaller than the plan's
-    return v[idx];
+    const bool mid = n <= MID_N && !b200rs_exp_env("B200RS_NO_MID_PATH", 0);
+    const Variant& production = mid ? Variants<ElemT>::mid_size() : Variants<ElemT>::full_size();
+#ifdef B200RS_EXPERIMENTS
+    if (const char* e = getenv(Variants<ElemT>::env())) {
+        int count = 0;
+        const Variant* v = Variants<ElemT>::list(&count);
+        const int idx = atoi(e);
+        // (a forced variant whose tiles are smaller than the plan's would overrun the look-back table)
+        if (idx >= 0 && idx < count && (uint64_t)v[idx].threads * v[idx].ipt >= min_tile_for(n)) return v[idx];
+    }
+#endif
+    return production;
 }
 
 struct SortPlan {
@@ -891,12 +907,12 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     if (n <= 1 || plan.passes == 0) return B200RS_OK;  // nothing to order
 
     b200rs_device_guard guard(dev);
-    if (n <= (uint64_t)SMALL_CAP && !n_dev && !(getenv("B200RS_NO_SMALL_PATH") && atoi(getenv("B200RS_NO_SMALL_PATH")))) {
+    if (n <= (uint64_t)SMALL_CAP && !n_dev && !b200rs_exp_env("B200RS_NO_SMALL_PATH", 0)) {
         // one launch of one CTA: all passes in shared memory (no histogram, no tickets, no look-back, no temp storage)
         char small_label[48];
         snprintf(small_label, sizeof(small_label), "small_sort_%s", what);
         const size_t smem = sizeof(SmallSortSmem<ElemT>);
-        B200RS_CUDA(cudaFuncSetAttribute(small_sort_kernel<ElemT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200RS_TRY(b200rs_kernel_setup(dev, (const void*)small_sort_kernel<ElemT>, smem));
         {
             b200rs_launch_scope scope(dev, small_label, n, 2ull * n * sizeof(ElemT));
             small_sort_kernel<ElemT><<<1, SMALL_THREADS, smem, dev->stream>>>(inout, (uint32_t)n, sort_bits, 0xffffffffu);
@@ -936,8 +952,7 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         if (((uintptr_t)inout & 15u) == 0) {
             // measured at 2^28 (tools/quick_perf.py): keys, 4 digits 0.190 ms against 0.270 with the packed counters (2 digits:
             // 0.176 / 0.182); pairs, 4 digits 0.330 / 0.350, 2 digits 0.354 / 0.326.  B200RS_HIST_VARIANT=0|1 forces one.
-            const char* hv = getenv("B200RS_HIST_VARIANT");
-            const int hist_variant = hv ? atoi(hv) : ((n > MID_N && (sizeof(ElemT) == 4 || plan.passes >= 3)) ? 1 : 0);  // small n: the 128 KiB table costs more to clear and drain than it saves
+            const int hist_variant = b200rs_exp_env("B200RS_HIST_VARIANT", (n > MID_N && (sizeof(ElemT) == 4 || plan.passes >= 3)) ? 1 : 0);  // small n: the 128 KiB table costs more to clear and drain than it saves
             if (hist_variant == 1) {
                 // 32-bit lane-private counters, one 1024-thread CTA per SM (keys: issue-bound with the packed counters)
                 const size_t smem = (size_t)plan.passes * RADIX * 32 * sizeof(uint32_t);
@@ -946,14 +961,14 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
                 if (blocks32 > (uint64_t)dev->num_sms) blocks32 = (uint64_t)dev->num_sms;
                 auto kernel = plan.passes == 4 ? digit_histogram32_kernel<ElemT, 4> : plan.passes == 3 ? digit_histogram32_kernel<ElemT, 3>
                             : plan.passes == 2 ? digit_histogram32_kernel<ElemT, 2> : digit_histogram32_kernel<ElemT, 1>;
-                B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B200RS_TRY(b200rs_kernel_setup(dev, (const void*)kernel, smem));
                 kernel<<<(unsigned)blocks32, HIST32_THREADS, smem, dev->stream>>>(inout, n, key_mask, ghist, n_dev, done_counter, pass_ctl);
             } else {
                 const uint64_t max_blocks = (uint64_t)dev->num_sms * 3;  // 3 x (512 threads, 64 KiB of counters) per SM, grid-stride beyond that
                 if (blocks > max_blocks) blocks = max_blocks;
                 auto kernel = plan.passes == 4 ? digit_histogram_kernel<ElemT, 4> : plan.passes == 3 ? digit_histogram_kernel<ElemT, 3>
                             : plan.passes == 2 ? digit_histogram_kernel<ElemT, 2> : digit_histogram_kernel<ElemT, 1>;
-                B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HIST_SMEM_BYTES));
+                B200RS_TRY(b200rs_kernel_setup(dev, (const void*)kernel, HIST_SMEM_BYTES));
                 kernel<<<(unsigned)blocks, HIST_THREADS, HIST_SMEM_BYTES, dev->stream>>>(inout, n, key_mask, 0x101u, ghist, n_dev, done_counter, pass_ctl);
             }
         } else {
@@ -968,13 +983,12 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         digit_start_kernel<<<1, RADIX, 0, dev->stream>>>(ghist, plan.passes, n, n_dev, pass_ctl);
     }
 
-    B200RS_CUDA(cudaFuncSetAttribute(var.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var.smem));
+    B200RS_TRY(b200rs_kernel_setup(dev, var.kernel, var.smem));
     // L2 prefetch distance of the scatter pass, in tiles.  Tickets are handed out at ~40 tiles per microsecond, so 64 tiles
     // ahead is ~1.5 us, longer than an HBM round trip; measured flat from 32 to 222 tiles (pairs 0.992 ms/pass against
     // 1.046 without), worse again from ~600 tiles on (the prefetched lines are evicted before use: 1.11 ms at 888).
     // B200RS_PF_TILES overrides (development knob; 0 switches the prefetch off).
-    uint32_t pf_tiles = var.gen == 2 ? 64u : 0u;
-    if (const char* e = getenv("B200RS_PF_TILES")) pf_tiles = (uint32_t)atoi(e);
+    uint32_t pf_tiles = (uint32_t)b200rs_exp_env("B200RS_PF_TILES", var.gen == 2 ? 64 : 0);
     ElemT* src = inout;
     ElemT* dst = alt;
     for (int p = 0; p < plan.passes; ++p) {
@@ -1066,7 +1080,7 @@ extern "C" int b200rs_partition_pairs(b200rs_device* dev, const b200rs_pair* in,
     B200RS_CUDA(cudaMemsetAsync(temp, 0, need, dev->stream));
     auto kernel = onesweep_kernel<uint2, PART_THREADS, PART_IPT, RANK_BALLOT, 3, true>;
     const size_t smem = sizeof(typename Cfg::Smem);
-    B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200RS_TRY(b200rs_kernel_setup(dev, (const void*)kernel, smem));
     uint32_t* ticket = reinterpret_cast<uint32_t*>(temp);
     uint64_t* lookback = reinterpret_cast<uint64_t*>(static_cast<char*>(temp) + 256);
     {
@@ -1098,7 +1112,7 @@ extern "C" int b200rs_scatter_pairs_to_parts(b200rs_device* dev, const b200rs_pa
     B200RS_CUDA(cudaMemsetAsync(temp, 0, need, dev->stream));
     auto kernel = onesweep_kernel<uint2, PART_THREADS, PART_IPT, RANK_BALLOT, 3, true, true>;
     const size_t smem = sizeof(typename Cfg::Smem);
-    B200RS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200RS_TRY(b200rs_kernel_setup(dev, (const void*)kernel, smem));
     uint32_t* ticket = reinterpret_cast<uint32_t*>(temp);
     uint64_t* lookback = reinterpret_cast<uint64_t*>(static_cast<char*>(temp) + 256);
     {
