@@ -9,7 +9,7 @@ REF    ?= /root/reference
 ARCH   := -gencode arch=compute_100a,code=sm_100a
 # make EXPERIMENTS=1: also compiles the measurement-only kernel variants and the B200RS_* environment knobs (tools/sweep.py);
 # the default (production) library contains neither.
-EXPFLAGS := $(if $(EXPERIMENTS),-DB200RS_EXPERIMENTS,)
+EXPFLAGS := $(if $(EXPERIMENTS),-DB200RS_EXPERIMENTS=$(EXPERIMENTS),)
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v -Iinclude $(EXPFLAGS)
 CSRC   := oclradixsort_b200/csrc
 SRCS   := $(CSRC)/b200rs_device.cu $(CSRC)/b200rs_scan.cu $(CSRC)/b200rs_sort.cu $(CSRC)/b200rs_host.cu $(CSRC)/b200rs_prims.cu
@@ -29,6 +29,18 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/b200rs_internal.h include/b200rs.h $(wildcard 
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+
+# Experiments build (measurement-only kernel variants + B200RS_* environment knobs), kept apart from the product:
+#   make experiments  ->  tools/_build/libb200rs_exp.so ;  B200RS_LIB=tools/_build/libb200rs_exp.so python tools/msd_probe.py ...
+#   make experiments EXPERIMENTS=2 also compiles the round-1 scatter-pass sweep lists (B200RS_KEYS_VARIANT / _PAIRS_VARIANT, tools/sweep.py)
+EXP_DIR  := tools/_build/exp
+EXP_OBJS := $(patsubst $(CSRC)/%.cu,$(EXP_DIR)/%.o,$(SRCS))
+$(EXP_DIR)/%.o: $(CSRC)/%.cu $(CSRC)/b200rs_internal.h include/b200rs.h $(wildcard $(CSRC)/*.cuh)
+	mkdir -p $(EXP_DIR)
+	$(NVCC) $(NVFLAGS) -DB200RS_EXPERIMENTS=$(or $(EXPERIMENTS),1) -c $< -o $@ 2> $(@:.o=.ptxas.log) || (cat $(@:.o=.ptxas.log); false)
+experiments: $(EXP_OBJS)
+	$(NVCC) $(ARCH) -shared -o tools/_build/libb200rs_exp.so $(EXP_OBJS)
+.PHONY: experiments
 
 oracle:
 	$(MAKE) -C oracle all

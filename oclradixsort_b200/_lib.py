@@ -10,7 +10,9 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200rs.so")
+# B200RS_LIB: developer tools only (tools/sweep.py, tools/msd_probe.py) -- points the binding at the experiments build
+# (make experiments -> tools/_build/libb200rs_exp.so).  The library itself reads no environment variable.
+LIB_PATH = os.environ.get("B200RS_LIB") or os.path.join(_HERE, "libb200rs.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200rs.h")
 
 c_dev = ctypes.c_void_p
@@ -45,6 +47,7 @@ SIGNATURES = {
     "b200rs_memcpy_d2d": (_int, [c_dev, _vp, _vp, _sz]),
     "b200rs_memset": (_int, [c_dev, _vp, _int, _sz]),
     "b200rs_sort_keys_u32": (_int, [c_dev, _vp, _u64, _int, _vp, _P(_sz)]),
+    "b200rs_sort_keys_u32_msd": (_int, [c_dev, _vp, _u64, _vp, _P(_sz), _P(_int)]),
     "b200rs_sort_pairs_u32": (_int, [c_dev, _vp, _u64, _int, _vp, _P(_sz)]),
     "b200rs_exclusive_scan_u32": (_int, [c_dev, _vp, _vp, _u64, _vp, _vp, _P(_sz)]),
     "b200rs_copy_u32": (_int, [c_dev, _vp, _vp, _u64]),

@@ -609,9 +609,10 @@ onesweep_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t 
 }
 
 #include "b200rs_onesweep2.cuh"
-#ifdef B200RS_EXPERIMENTS
+#if defined(B200RS_EXPERIMENTS) && B200RS_EXPERIMENTS >= 2
 #include "b200rs_onesweep3.cuh"
 #endif
+#include "b200rs_msd.cuh"
 
 // =================================================================================================
 // Small inputs: the whole sort in ONE launch of ONE CTA.
@@ -732,7 +733,7 @@ template <> struct Variants<uint32_t> {
     // swizzled body for passes flagged PASS_REGULAR
     static const Variant& full_size() { static const Variant v = B200RS_VARIANT2D(uint32_t, 256, 35, 4); return v; }
     static const Variant& mid_size() { static const Variant v = B200RS_VARIANT2(uint32_t, 256, 8, 4, WO_ELEM, ORDER_LATE, LOAD_LDG); return v; }  // 2048-key tiles
-#ifdef B200RS_EXPERIMENTS
+#if defined(B200RS_EXPERIMENTS) && B200RS_EXPERIMENTS >= 2  // the full round-1 sweep list (make EXPERIMENTS=2; slow to compile)
     static const Variant* list(int* count) {
         static const Variant v[] = {
             B200RS_VARIANT(uint32_t, 512, 24, RANK_BALLOT, 3),  // default
@@ -792,7 +793,7 @@ template <> struct Variants<uint2> {
     // 320 threads x 20 pairs = 25 pairs per digit on average (odd, see the keys note), 3 CTAs/SM
     static const Variant& full_size() { static const Variant v = B200RS_VARIANT2(uint2, 320, 20, 3, WO_ELEM, ORDER_LATE, LOAD_LDG); return v; }
     static const Variant& mid_size() { static const Variant v = B200RS_VARIANT2(uint2, 256, 8, 4, WO_ELEM, ORDER_LATE, LOAD_LDG); return v; }  // 2048-pair tiles
-#ifdef B200RS_EXPERIMENTS
+#if defined(B200RS_EXPERIMENTS) && B200RS_EXPERIMENTS >= 2
     static const Variant* list(int* count) {
         static const Variant v[] = {
             B200RS_VARIANT(uint2, 384, 16, RANK_BALLOT, 3),  // default
@@ -849,7 +850,7 @@ template <typename ElemT>
 const Variant& pick_variant(uint64_t n) {
     const bool mid = n <= MID_N && !b200rs_exp_env("B200RS_NO_MID_PATH", 0);
     const Variant& production = mid ? Variants<ElemT>::mid_size() : Variants<ElemT>::full_size();
-#ifdef B200RS_EXPERIMENTS
+#if defined(B200RS_EXPERIMENTS) && B200RS_EXPERIMENTS >= 2
     if (const char* e = getenv(Variants<ElemT>::env())) {
         int count = 0;
         const Variant* v = Variants<ElemT>::list(&count);
@@ -865,16 +866,31 @@ struct SortPlan {
     int passes;
     size_t alt_off, hist_off, ticket_off, lookback_off, total_bytes;
     size_t clear_off, clear_bytes;  // histograms + tickets + look-back table are zeroed per call
+    // key-only MSD path (b200rs_msd.cuh), present when msd_candidate(): [joint histogram | control words] are zeroed per call
+    bool msd;
+    size_t msd_joint_off, msd_ctl_off, msd_bucket_off_off, msd_cursor2_off, msd_cursor1_off, msd_tiles_off;
 };
 
+// The MSD path is tried for full 32-bit key sorts of this size range (below: per-bucket fixed costs of the counting step
+// dominate; above: a uniform input's buckets exceed its shared memory and element indices are kept in 32 bits).
+constexpr uint64_t MSD_MIN_N = 1ull << 40 /* automatic selection off until the path wins (first measurement: 2.96 ms vs 2.85 at 2^28) */, MSD_MAX_N = (1ull << 30) - 1;
+constexpr uint32_t MSD_MIN_P_TILE = 4096;  // smallest partition tile among the compiled shapes: the tile table is sized for it
+enum MsdMode { MSD_AUTO = 0, MSD_FORCED = 1 };  // MSD_FORCED: b200rs_sort_keys_u32_msd -- no lower size limit
 template <typename ElemT>
-int make_plan(uint64_t n, int sort_bits, SortPlan* p) {
+inline bool msd_candidate(uint64_t n, int sort_bits, int mode) {
+    return sizeof(ElemT) == 4 && sort_bits == 32 && n <= MSD_MAX_N && (mode == MSD_FORCED ? n >= 2 : n >= MSD_MIN_N);
+}
+
+template <typename ElemT>
+int make_plan(uint64_t n, int sort_bits, SortPlan* p, int msd_mode = MSD_AUTO) {
     if (sort_bits < 0 || sort_bits > 32) return B200RS_ERR_INVALID_ARGUMENT;
     const uint64_t tiles = (n + min_tile_for(n) - 1) / min_tile_for(n);
     if (tiles > 0x7fffffffull) return B200RS_ERR_TOO_LARGE;
     p->passes = (sort_bits + RADIX_BITS - 1) / RADIX_BITS;
     size_t off = 0;
-    p->alt_off = off;      off += b200rs_align_up((size_t)n * sizeof(ElemT), 256);
+    p->msd = msd_candidate<ElemT>(n, sort_bits, msd_mode);
+    // (MSD: the intermediate buffer pads every first-pass bucket to a 16-byte boundary, see msd_mid_start)
+    p->alt_off = off;      off += b200rs_align_up(((size_t)n + (p->msd ? 1024 : 0)) * sizeof(ElemT), 256);
     p->clear_off = off;
     p->hist_off = off;     off += b200rs_align_up(sizeof(unsigned long long) * MAX_PASSES * RADIX, 256);
     p->ticket_off = off;   off += 256;
@@ -887,16 +903,149 @@ int make_plan(uint64_t n, int sort_bits, SortPlan* p) {
         off += b200rs_align_up(gen1 > gen2 ? gen1 : gen2, 256);
     }
     p->clear_bytes = off - p->clear_off;
+    if (p->msd) {
+        p->msd_joint_off = off;      off += (size_t)MSD_BUCKETS * sizeof(uint32_t);
+        p->msd_ctl_off = off;        off += 256;
+        p->msd_bucket_off_off = off; off += b200rs_align_up((size_t)(MSD_BUCKETS + 1) * sizeof(uint32_t), 256);
+        p->msd_cursor2_off = off;    off += (size_t)MSD_BUCKETS * sizeof(uint32_t);
+        p->msd_cursor1_off = off;    off += b200rs_align_up((size_t)RADIX * sizeof(uint32_t), 256);
+        p->msd_tiles_off = off;      off += b200rs_align_up(((size_t)(n / MSD_MIN_P_TILE) + RADIX + 1) * sizeof(MsdTile), 256);
+    }
     p->total_bytes = off ? off : 256;
+    return B200RS_OK;
+}
+
+// ---- key-only MSD path: host side ---------------------------------------------------------------------
+struct MsdPartitionShape {
+    const void* p1;
+    const void* p2;
+    int threads, tile;
+    size_t smem;
+    const char* name;
+};
+#define B200RS_MSD_P(THREADS, VPT, CAP, MIN_CTAS)                                                                                         \
+    MsdPartitionShape{(const void*)msd_partition_kernel<THREADS, VPT, CAP, MIN_CTAS, false>, (const void*)msd_partition_kernel<THREADS, VPT, CAP, MIN_CTAS, true>, \
+                      THREADS, THREADS * VPT * 4, sizeof(typename MsdPartitionConfig<THREADS, VPT, CAP>::Smem), #THREADS "x" #VPT "x4/cap" #CAP "/" #MIN_CTAS}
+struct MsdBucketShape {
+    const void* kernel;
+    int threads, cap;
+    size_t smem;
+    const char* name;
+};
+#define B200RS_MSD_F(THREADS, IPT, MIN_CTAS) \
+    MsdBucketShape{(const void*)msd_bucket_kernel<THREADS, IPT, MIN_CTAS>, THREADS, THREADS * IPT, MsdBucketConfig<THREADS, IPT>::SMEM_BYTES, #THREADS "x" #IPT "/" #MIN_CTAS}
+
+inline const MsdPartitionShape& msd_partition_shape() {
+    static const MsdPartitionShape production = B200RS_MSD_P(256, 8, 64, 3);
+#ifdef B200RS_EXPERIMENTS
+    static const MsdPartitionShape v[] = {
+        B200RS_MSD_P(256, 8, 64, 3),   // 0: 8192-key tiles, 64 KiB of bins
+        B200RS_MSD_P(256, 6, 48, 4),   // 1: 6144-key tiles, 48 KiB
+        B200RS_MSD_P(512, 4, 64, 3),   // 2
+        B200RS_MSD_P(512, 3, 48, 4),   // 3
+        B200RS_MSD_P(384, 4, 48, 4),   // 4
+        B200RS_MSD_P(256, 4, 40, 5),   // 5: 4096-key tiles, 40 KiB
+        B200RS_MSD_P(1024, 4, 112, 1), // 6: 16384-key tiles, one CTA per SM
+        B200RS_MSD_P(512, 6, 80, 2),   // 7: 12288-key tiles
+    };
+    const int idx = b200rs_exp_env("B200RS_MSD_P", 0);
+    if (idx >= 0 && idx < (int)(sizeof(v) / sizeof(v[0]))) return v[idx];
+#endif
+    return production;
+}
+// the counting step keeps a whole bucket in registers + shared memory: the smallest shape that holds the largest bucket
+inline const MsdBucketShape* msd_bucket_shape(uint32_t max_bucket) {
+    static const MsdBucketShape v[] = {
+        B200RS_MSD_F(256, 24, 3),  // 6144 keys, 72 KiB
+        B200RS_MSD_F(256, 36, 2),  // 9216 keys, 84 KiB
+        B200RS_MSD_F(256, 48, 2),  // 12288 keys, 96 KiB
+    };
+#ifdef B200RS_EXPERIMENTS
+    static const MsdBucketShape x[] = {B200RS_MSD_F(256, 20, 3), B200RS_MSD_F(256, 32, 2), B200RS_MSD_F(256, 28, 3)};
+    const int idx = b200rs_exp_env("B200RS_MSD_F", -1);
+    if (idx >= 3 && idx < 6 && max_bucket <= (uint32_t)x[idx - 3].cap) return &x[idx - 3];
+    if (idx >= 0 && idx < 3 && max_bucket <= (uint32_t)v[idx].cap) return &v[idx];
+#endif
+    for (const MsdBucketShape& f : v)
+        if (max_bucket <= (uint32_t)f.cap) return &f;
+    return nullptr;
+}
+constexpr uint32_t MSD_MAX_BUCKET = 256 * 48;
+
+// Returns B200RS_OK when the keys were sorted here, MSD_NOT_ELIGIBLE when the input is not eligible (the caller runs the LSD
+// path), an error code otherwise.  ONE host round trip: the choice between the two paths depends on the joint histogram, and both
+// paths are whole kernel chains, so the host waits for H + PL (about a tenth of the sort) and reads two words.
+constexpr int MSD_NOT_ELIGIBLE = -1000;
+int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, const SortPlan& plan) {
+    if (((uintptr_t)inout & 15u) != 0 || b200rs_exp_env("B200RS_NO_MSD", 0)) return MSD_NOT_ELIGIBLE;
+    if (!dev->pinned_word) B200RS_CUDA(cudaHostAlloc((void**)&dev->pinned_word, 64, cudaHostAllocDefault));
+    uint32_t* alt = reinterpret_cast<uint32_t*>(base + plan.alt_off);
+    uint32_t* joint = reinterpret_cast<uint32_t*>(base + plan.msd_joint_off);
+    uint32_t* ctl = reinterpret_cast<uint32_t*>(base + plan.msd_ctl_off);
+    uint32_t* bucket_off = reinterpret_cast<uint32_t*>(base + plan.msd_bucket_off_off);
+    uint32_t* cursor2 = reinterpret_cast<uint32_t*>(base + plan.msd_cursor2_off);
+    uint32_t* cursor1 = reinterpret_cast<uint32_t*>(base + plan.msd_cursor1_off);
+    MsdTile* tiles = reinterpret_cast<MsdTile*>(base + plan.msd_tiles_off);
+    const MsdPartitionShape& ps = msd_partition_shape();
+    const uint32_t n32 = (uint32_t)n;
+
+    B200RS_CUDA(cudaMemsetAsync(joint, 0, (size_t)MSD_BUCKETS * sizeof(uint32_t) + 256, dev->stream));  // joint histogram + control words
+    B200RS_TRY(b200rs_kernel_setup(dev, (const void*)msd_hist16_kernel, MSD_HIST_SMEM));
+    {
+        b200rs_launch_scope scope(dev, "msd_hist16_keys", n, n * 4ull);
+        const uint64_t per_block = (uint64_t)MSD_HIST_THREADS * MSD_HIST_VECS * 4;
+        uint64_t blocks = (n + per_block - 1) / per_block;
+        if (blocks > (uint64_t)dev->num_sms) blocks = (uint64_t)dev->num_sms;
+        msd_hist16_kernel<<<(unsigned)blocks, MSD_HIST_THREADS, MSD_HIST_SMEM, dev->stream>>>(inout, n, reinterpret_cast<unsigned long long*>(joint), ctl);
+    }
+    {
+        b200rs_launch_scope scope(dev, "msd_plan", MSD_BUCKETS, (uint64_t)MSD_BUCKETS * 12);
+        msd_plan_kernel<<<1, MSD_PLAN_THREADS, 0, dev->stream>>>(joint, n32, (uint32_t)ps.tile, MSD_MAX_BUCKET, bucket_off, cursor2, cursor1, tiles, ctl);
+    }
+    B200RS_CUDA(cudaGetLastError());
+    B200RS_CUDA(cudaMemcpyAsync(dev->pinned_word, ctl, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, dev->stream));
+    B200RS_CUDA(cudaStreamSynchronize(dev->stream));
+    if (dev->pinned_word[MSD_CTL_INELIGIBLE]) return MSD_NOT_ELIGIBLE;
+    const MsdBucketShape* fs = msd_bucket_shape(dev->pinned_word[MSD_CTL_MAX_BUCKET]);
+    if (!fs) return MSD_NOT_ELIGIBLE;
+
+    B200RS_TRY(b200rs_kernel_setup(dev, ps.p1, ps.smem));
+    B200RS_TRY(b200rs_kernel_setup(dev, ps.p2, ps.smem));
+    B200RS_TRY(b200rs_kernel_setup(dev, fs->kernel, fs->smem));
+    const uint32_t* in1 = inout;
+    const MsdTile* no_tiles = nullptr;
+    int shift1 = 24, shift2 = 16;
+    const uint32_t* ctl_c = ctl;
+    {
+        b200rs_launch_scope scope(dev, "msd_partition_keys_pass0", n, 8ull * n);
+        void* args[] = {&in1, &alt, (void*)&n32, &shift1, &cursor1, &no_tiles, &ctl_c};
+        B200RS_CUDA(cudaLaunchKernel(ps.p1, dim3((unsigned)((n + ps.tile - 1) / ps.tile)), dim3(ps.threads), args, ps.smem, dev->stream));
+    }
+    {
+        b200rs_launch_scope scope(dev, "msd_partition_keys_pass1", n, 8ull * n);
+        const uint32_t* in2 = alt;
+        const MsdTile* tiles_c = tiles;
+        void* args[] = {&in2, &inout, (void*)&n32, &shift2, &cursor2, &tiles_c, &ctl_c};
+        B200RS_CUDA(cudaLaunchKernel(ps.p2, dim3((unsigned)(n / ps.tile + RADIX)), dim3(ps.threads), args, ps.smem, dev->stream));
+    }
+    {
+        b200rs_launch_scope scope(dev, "msd_bucket_keys", n, 8ull * n);
+        const uint32_t* off_c = bucket_off;
+        uint32_t minus_one = 0xffffffffu;
+        void* args[] = {&inout, &off_c, &minus_one};
+        B200RS_CUDA(cudaLaunchKernel(fs->kernel, dim3(MSD_BUCKETS), dim3(fs->threads), args, fs->smem, dev->stream));
+    }
+    B200RS_CUDA(cudaGetLastError());
     return B200RS_OK;
 }
 
 template <typename ElemT>
 int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes, const char* what,
-              const unsigned long long* n_dev = nullptr) {
+              const unsigned long long* n_dev = nullptr, int msd_mode = MSD_AUTO, int* msd_used = nullptr) {
     if (!dev || !temp_bytes) return B200RS_ERR_INVALID_ARGUMENT;
+    if (msd_used) *msd_used = 0;
     SortPlan plan;
-    B200RS_TRY(make_plan<ElemT>(n, sort_bits, &plan));
+    B200RS_TRY(make_plan<ElemT>(n, sort_bits, &plan, msd_mode));
     if (!temp) {
         *temp_bytes = plan.total_bytes;
         return B200RS_OK;
@@ -907,7 +1056,7 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     if (n <= 1 || plan.passes == 0) return B200RS_OK;  // nothing to order
 
     b200rs_device_guard guard(dev);
-    if (n <= (uint64_t)SMALL_CAP && !n_dev && !b200rs_exp_env("B200RS_NO_SMALL_PATH", 0)) {
+    if (n <= (uint64_t)SMALL_CAP && !n_dev && msd_mode != MSD_FORCED && !b200rs_exp_env("B200RS_NO_SMALL_PATH", 0)) {
         // one launch of one CTA: all passes in shared memory (no histogram, no tickets, no look-back, no temp storage)
         char small_label[48];
         snprintf(small_label, sizeof(small_label), "small_sort_%s", what);
@@ -920,10 +1069,15 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         B200RS_CUDA(cudaGetLastError());
         return B200RS_OK;
     }
+    char* base = static_cast<char*>(temp);
+    if (plan.msd && !n_dev) {
+        const int r = sort_keys_msd(dev, reinterpret_cast<uint32_t*>(inout), n, base, plan);
+        if (r == B200RS_OK && msd_used) *msd_used = 1;
+        if (r != MSD_NOT_ELIGIBLE) return r;
+    }
     const Variant& var = pick_variant<ElemT>(n);
     const uint64_t tile_elems = (uint64_t)var.threads * var.ipt;
     const uint32_t num_tiles = (uint32_t)((n + tile_elems - 1) / tile_elems);
-    char* base = static_cast<char*>(temp);
     ElemT* alt = reinterpret_cast<ElemT*>(base + plan.alt_off);
     unsigned long long* ghist = reinterpret_cast<unsigned long long*>(base + plan.hist_off);
     uint32_t* tickets = reinterpret_cast<uint32_t*>(base + plan.ticket_off);
@@ -1259,6 +1413,10 @@ extern "C" int b200rs_ipc_release(b200rs_device* dev, void* ptr) {
 
 extern "C" int b200rs_sort_keys_u32(b200rs_device* dev, uint32_t* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes) {
     return sort_impl<uint32_t>(dev, inout, n, sort_bits, temp, temp_bytes, "keys");
+}
+
+extern "C" int b200rs_sort_keys_u32_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, void* temp, size_t* temp_bytes, int* used) {
+    return sort_impl<uint32_t>(dev, inout, n, 32, temp, temp_bytes, "keys", nullptr, MSD_FORCED, used);
 }
 
 extern "C" int b200rs_sort_pairs_u32(b200rs_device* dev, b200rs_pair* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes) {
