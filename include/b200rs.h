@@ -99,9 +99,9 @@ int b200rs_sort_keys_u32(b200rs_device* dev, uint32_t* inout, uint64_t n, int so
 /*
  * The same sort (all 32 bits) with the algorithm chosen by the caller: the most-significant-digit-first pipeline that
  * b200rs_sort_keys_u32 picks by itself for large inputs (joint histogram of the top 16 bits, two unstable 8-bit partition
- * passes, counting sort of every bucket in shared memory; csrc/b200rs_msd.cuh) is tried at ANY n >= 1.  *used = 1 when it
- * sorted the keys, 0 when the input was not eligible (a top-16 bucket larger than the counting step's shared memory,
- * inout not 16-byte aligned, n >= 2^30) and the LSD path did.  Same result either way: key-only, so nothing depends
+ * passes, counting sort of every bucket in shared memory; csrc/b200rs_msd.cuh) is tried at ANY n >= 2.  *used = 1 when it
+ * sorted the keys, 0 when the input was not eligible (more than 12257 keys share their top 16 bits, inout not 16-byte
+ * aligned, n >= 2^30) and the LSD path did.  Same result either way: key-only, so nothing depends
  * on stability.  Size query as above (this entry may need more temp than b200rs_sort_keys_u32 for the same n).
  * Blocks the host once (the eligibility test).  Pprims::radixSort(device, Buffer<u32>&, n), Pprims.cpp:304-406.
  */

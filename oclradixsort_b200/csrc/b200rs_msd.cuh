@@ -38,6 +38,11 @@ enum MsdCtl {
     MSD_CTL_P2_TILES = 2,    // tiles of the second partition pass
     MSD_CTL_WORDS = 8,
 };
+enum MsdIneligible {
+    MSD_WHY_CHECKSUM = 1,  // a 16-bit counter of H wrapped
+    MSD_WHY_BUCKET = 2,    // PL: a bucket is larger than F's capacity
+    MSD_WHY_EARLY = 4,     // H: a CTA's own count of one bucket already exceeds F's capacity -- H stops early
+};
 
 // =================================================================================================
 // H: joint histogram of the top 16 bits
@@ -52,9 +57,15 @@ constexpr int MSD_HIST_THREADS = 1024;
 constexpr int MSD_HIST_VECS = 4;  // LDG.128 in flight per thread
 constexpr size_t MSD_HIST_SMEM = (size_t)(MSD_BUCKETS / 2) * sizeof(uint32_t);
 
+// Every MSD_HIST_CHECK_ROUNDS rounds the CTA looks for a counter above `bucket_cap`: its own share of one bucket already
+// exceeds what F can take, so the input is not eligible and the CTA stops (skewed inputs make this kernel slow -- lanes
+// that hit the same counter are serialised -- and would be sent to the LSD path anyway).  The decision is local: the
+// CTAs see statistically the same data (grid-stride rounds), so they all stop within a check or two of each other,
+// and nobody waits for a global flag.
+constexpr int MSD_HIST_CHECK_ROUNDS = 16;  // 256 Ki keys per CTA between checks
 __global__ void __launch_bounds__(MSD_HIST_THREADS, 1)
 msd_hist16_kernel(const uint32_t* __restrict__ in, uint64_t n, unsigned long long* __restrict__ joint2 /*[32768] pairs of u32 counters*/,
-                  uint32_t* __restrict__ ctl) {
+                  uint32_t* __restrict__ ctl, uint32_t bucket_cap) {
     extern __shared__ __align__(16) uint32_t msd_tab[];  // [32768]
     __shared__ uint32_t s_sum[MSD_HIST_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -70,6 +81,7 @@ msd_hist16_kernel(const uint32_t* __restrict__ in, uint64_t n, unsigned long lon
     const uint64_t nvec = n / 4;
     const uint4* in4 = reinterpret_cast<const uint4*>(in);
     const uint64_t round_vecs = (uint64_t)MSD_HIST_THREADS * MSD_HIST_VECS;
+    int rounds = 0;
     for (uint64_t base = (uint64_t)blockIdx.x * round_vecs; base < nvec; base += (uint64_t)gridDim.x * round_vecs) {
         uint4 q[MSD_HIST_VECS];
         bool have[MSD_HIST_VECS];
@@ -91,6 +103,28 @@ msd_hist16_kernel(const uint32_t* __restrict__ in, uint64_t n, unsigned long lon
             } else if (have[u]) {
                 count1(q[u].x, 1u); count1(q[u].y, 1u); count1(q[u].z, 1u); count1(q[u].w, 1u);
                 counted += 4;
+            }
+        }
+        if (++rounds % MSD_HIST_CHECK_ROUNDS == 0) {  // (every thread of the CTA runs the same number of rounds)
+            __syncthreads();
+            uint32_t over = 0, seen_now = 0;
+            for (int w = tid; w < MSD_BUCKETS / 2; w += MSD_HIST_THREADS) {
+                const uint32_t x = msd_tab[w];
+                seen_now += (x & 0xffffu) + (x >> 16);
+                over |= ((x & 0xffffu) > bucket_cap || (x >> 16) > bucket_cap) ? 1u : 0u;
+            }
+            // a counter that wrapped since the last check (extreme skew) shows up as a checksum mismatch, as at the end
+            uint32_t dd = seen_now - counted;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+            if (lane == 0) s_sum[tid >> 5] = dd;
+            __syncthreads();
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < MSD_HIST_THREADS / 32; ++w) tot += s_sum[w];
+            if (__syncthreads_or((int)(over | (tot != 0u)))) {  // the histogram is abandoned: nobody will use it
+                if (tid == 0) atomicOr(&ctl[MSD_CTL_INELIGIBLE], (uint32_t)MSD_WHY_EARLY);
+                return;
             }
         }
     }
@@ -116,7 +150,7 @@ msd_hist16_kernel(const uint32_t* __restrict__ in, uint64_t n, unsigned long lon
     if (tid == 0) {
         uint32_t t = 0;
         for (int w = 0; w < MSD_HIST_THREADS / 32; ++w) t += s_sum[w];
-        if (t != 0) atomicOr(&ctl[MSD_CTL_INELIGIBLE], 1u);
+        if (t != 0) atomicOr(&ctl[MSD_CTL_INELIGIBLE], (uint32_t)MSD_WHY_CHECKSUM);
     }
 }
 
@@ -127,105 +161,69 @@ struct MsdTile {
     uint32_t start;  // first key of the tile in the intermediate buffer (a multiple of 4)
     uint32_t meta;   // (bucket of the first partition pass << 16) | keys in the tile
 };
-constexpr int MSD_PLAN_THREADS = 1024;
-constexpr int MSD_PLAN_BINS = MSD_BUCKETS / MSD_PLAN_THREADS;  // 64 consecutive bins per thread
-
 // Layout of the intermediate buffer (output of P1, input of P2): bucket b of the first pass starts at
 // (final start of b rounded down to a multiple of 4) + 4 b, so every tile of P2 can be read with aligned 128-bit loads;
 // buckets cannot overlap (the rounding loses at most 3, the 4 b term adds 4 per bucket); the buffer needs n + 1024 keys.
 __device__ __forceinline__ uint32_t msd_mid_start(uint32_t final_start, uint32_t bucket) { return (final_start & ~3u) + 4u * bucket; }
 
-__global__ void __launch_bounds__(MSD_PLAN_THREADS, 1)
-msd_plan_kernel(const uint32_t* __restrict__ joint /*[65536]*/, uint32_t n, uint32_t tile_keys /* P2 tile */, uint32_t bucket_cap /* F capacity */,
+// PL-a: 256 CTAs x 256 threads, CTA b sums the 256 joint bins of first-pass bucket b (-> hist3[b]) and folds the largest
+// bin into the control words.
+__global__ void __launch_bounds__(RADIX)
+msd_plan_sums_kernel(const uint32_t* __restrict__ joint, uint32_t* __restrict__ hist3 /*[256]*/, uint32_t* __restrict__ ctl) {
+    __shared__ uint32_t s_sum[RADIX / 32], s_max[RADIX / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t x = __ldcg(joint + blockIdx.x * RADIX + tid);
+    uint32_t sum = x, mx = x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_sum[warp] = sum; s_max[warp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+        sum = 0; mx = 0;
+        for (int w = 0; w < RADIX / 32; ++w) { sum += s_sum[w]; mx = max(mx, s_max[w]); }
+        hist3[blockIdx.x] = sum;
+        atomicMax(&ctl[MSD_CTL_MAX_BUCKET], mx);
+    }
+}
+
+// PL-b: 256 CTAs x 256 threads.  Every CTA scans hist3 (256 values) for the bucket starts and the first tile of every
+// bucket; CTA b then scans its own 256 joint bins into bucket_off / cursor2 and writes the tile entries of bucket b.
+__global__ void __launch_bounds__(RADIX)
+msd_plan_kernel(const uint32_t* __restrict__ joint /*[65536]*/, const uint32_t* __restrict__ hist3, uint32_t n, uint32_t tile_keys /* P2 tile */,
+                uint32_t bucket_cap /* F capacity */,
                 uint32_t* __restrict__ bucket_off /*[65537]: final start of every top-16 bucket*/,
                 uint32_t* __restrict__ cursor2 /*[65536]: = bucket_off, consumed by P2*/,
                 uint32_t* __restrict__ cursor1 /*[256]: start of every P1 bucket in the intermediate buffer, consumed by P1*/,
                 MsdTile* __restrict__ tiles, uint32_t* __restrict__ ctl) {
-    __shared__ uint32_t s_warp[MSD_PLAN_THREADS / 32];
-    __shared__ uint32_t s_max[MSD_PLAN_THREADS / 32];
-    __shared__ uint32_t s_start3[257];      // final start of every byte-3 bucket
-    __shared__ uint32_t s_tile_first[257];  // first tile of every byte-3 bucket
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // 64 consecutive bins per thread, read as 16 x uint4; lanes are 256 B apart (the table is 256 KiB, read once, from L2)
-    const uint4* j4 = reinterpret_cast<const uint4*>(joint) + (size_t)tid * (MSD_PLAN_BINS / 4);
-    uint32_t sum = 0, mx = 0;
-#pragma unroll 4
-    for (int i = 0; i < MSD_PLAN_BINS / 4; ++i) {
-        const uint4 v = __ldcg(j4 + i);
-        sum += (v.x + v.y) + (v.z + v.w);
-        mx = max(max(mx, max(v.x, v.y)), max(v.z, v.w));
-    }
-    uint32_t inc = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += y;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 31) s_warp[warp] = inc;
-    if (lane == 0) s_max[warp] = mx;
-    __syncthreads();
-    uint32_t base = 0;
-    for (int w = 0; w < warp; ++w) base += s_warp[w];
-    uint32_t run = base + inc - sum;  // exclusive prefix of this thread's first bin
-    if ((tid & 3) == 0) s_start3[tid >> 2] = run;  // bins 256 b .. 256 b + 255 belong to byte-3 bucket b = tid / 4
-    if (tid == 0) s_start3[256] = n;
-    uint4* o4 = reinterpret_cast<uint4*>(bucket_off) + (size_t)tid * (MSD_PLAN_BINS / 4);
-    uint4* c4 = reinterpret_cast<uint4*>(cursor2) + (size_t)tid * (MSD_PLAN_BINS / 4);
-#pragma unroll 4
-    for (int i = 0; i < MSD_PLAN_BINS / 4; ++i) {
-        const uint4 v = __ldcg(j4 + i);
-        uint4 o;
-        o.x = run; run += v.x;
-        o.y = run; run += v.y;
-        o.z = run; run += v.z;
-        o.w = run; run += v.w;
-        o4[i] = o;
-        c4[i] = o;
-    }
-    if (tid == 0) bucket_off[MSD_BUCKETS] = n;
-    __syncthreads();
-    // byte-3 buckets: cursors of the first pass, tiles of the second
-    if (tid < 256) {
-        const uint32_t start = s_start3[tid], size = s_start3[tid + 1] - start;
-        cursor1[tid] = msd_mid_start(start, (uint32_t)tid);
-        const uint32_t t = (size + tile_keys - 1) / tile_keys;
-        uint32_t tinc = t;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, tinc, d);
-            if (lane >= d) tinc += y;
-        }
-        if (lane == 31) s_warp[warp] = tinc;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        uint32_t tb = 0;
-        for (int w = 0; w < warp; ++w) tb += s_warp[w];
-        s_tile_first[tid] = tb + tinc - t;
-        if (tid == 255) s_tile_first[256] = tb + tinc;
+    __shared__ uint32_t scratch[RADIX / 32];
+    __shared__ uint32_t s_bcast[4];
+    const int tid = threadIdx.x;
+    const uint32_t b = blockIdx.x;
+    const uint32_t size3 = __ldcg(hist3 + tid);
+    const uint32_t start3 = block_exclusive_scan_256<uint32_t>(size3, scratch, tid);          // final start of first-pass bucket tid
+    const uint32_t t3 = (size3 + tile_keys - 1) / tile_keys;
+    const uint32_t tile_first = block_exclusive_scan_256<uint32_t>(t3, scratch, tid);          // first P2 tile of bucket tid
+    if ((uint32_t)tid == b) { s_bcast[0] = start3; s_bcast[1] = size3; s_bcast[2] = tile_first; s_bcast[3] = t3; }
+    if (b == 0) cursor1[tid] = msd_mid_start(start3, (uint32_t)tid);
+    if (b == 0 && tid == RADIX - 1) {
+        ctl[MSD_CTL_P2_TILES] = tile_first + t3;
+        bucket_off[MSD_BUCKETS] = n;
+        if (__ldcg(ctl + MSD_CTL_MAX_BUCKET) > bucket_cap) atomicOr(&ctl[MSD_CTL_INELIGIBLE], (uint32_t)MSD_WHY_BUCKET);
     }
     __syncthreads();
-    const uint32_t total_tiles = s_tile_first[256];
-    for (uint32_t t = tid; t < total_tiles; t += MSD_PLAN_THREADS) {
-        // bucket of tile t: the last b with tile_first[b] <= t (binary search over 256 entries; empty buckets are skipped by construction)
-        uint32_t lo = 0, hi = 256;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s_tile_first[mid] <= t) lo = mid; else hi = mid;
-        }
-        const uint32_t b = lo, k = t - s_tile_first[b];
-        const uint32_t start = s_start3[b], size = s_start3[b + 1] - start;
+    const uint32_t my_start = s_bcast[0], my_size = s_bcast[1], my_tile0 = s_bcast[2], my_tiles = s_bcast[3];
+    const uint32_t x = __ldcg(joint + b * RADIX + tid);
+    const uint32_t off = my_start + block_exclusive_scan_256<uint32_t>(x, scratch, tid);
+    bucket_off[b * RADIX + tid] = off;
+    cursor2[b * RADIX + tid] = off;
+    for (uint32_t k = tid; k < my_tiles; k += RADIX) {
         MsdTile e;
-        e.start = msd_mid_start(start, b) + k * tile_keys;
-        e.meta = (b << 16) | min(tile_keys, size - k * tile_keys);
-        tiles[t] = e;
-    }
-    if (tid == 0) {
-        uint32_t m = 0;
-        for (int w = 0; w < MSD_PLAN_THREADS / 32; ++w) m = max(m, s_max[w]);
-        ctl[MSD_CTL_MAX_BUCKET] = m;
-        ctl[MSD_CTL_P2_TILES] = total_tiles;
-        if (m > bucket_cap) atomicOr(&ctl[MSD_CTL_INELIGIBLE], 2u);
+        e.start = msd_mid_start(my_start, b) + k * tile_keys;
+        e.meta = (b << 16) | min(tile_keys, my_size - k * tile_keys);
+        tiles[my_tile0 + k] = e;
     }
 }
 
@@ -299,35 +297,77 @@ msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out
                 key[v][c] = j < count ? in[start + j] : 0u;
             }
     }
-    __syncthreads();
 
     // ---- claim: rank inside the digit's bin; keys below the capacity go straight to their slot ----
+    // The 128 keys of one vector (4 per lane) are tested together: if they all share the digit -- presorted input -- lane 0
+    // claims for the whole warp; otherwise the four atomics of a lane are issued back to back.
     const uint32_t cnt_base = smem_addr(&s.cnt[0]), bins_base = smem_addr(&s.bins[0]);
     const uint32_t prmt_sel = 0x4440u | (uint32_t)(shift >> 3);
     auto claim_all = [&](uint32_t counters, bool sparse) {
 #pragma unroll
-        for (int v = 0; v < VPT; ++v)
+        for (int v = 0; v < VPT; ++v) {
+            uint32_t d[4], r[4];
+            bool live[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const bool live = full || (uint32_t)(v * THREADS + tid) * 4 + c < count;
-                const uint32_t d = __byte_perm(key[v][c], 0u, prmt_sel);
-                const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
-                uint32_t r;
-                if (__all_sync(0xffffffffu, live && d == d0)) {
-                    // the warp's 32 keys share the digit: one atomic for all of them
-                    uint32_t b = 0;
-                    if (lane == 0) b = atom_add_shared(counters + 4u * d0, 32u);
-                    r = __shfl_sync(0xffffffffu, b, 0) + (uint32_t)lane;
-                } else {
-                    r = live ? atom_add_shared(counters + 4u * d, 1u) : 0xffffffffu;
-                }
+                live[c] = full || (uint32_t)(v * THREADS + tid) * 4 + c < count;
+                d[c] = __byte_perm(key[v][c], 0u, prmt_sel);
+            }
+            const uint32_t d0 = __shfl_sync(0xffffffffu, d[0], 0);
+            const bool same = live[3] && ((d[0] ^ d0) | (d[1] ^ d0) | (d[2] ^ d0) | (d[3] ^ d0)) == 0;  // (live[3] implies live[0..2])
+            if (__all_sync(0xffffffffu, same)) {
+                uint32_t b = 0;
+                if (lane == 0) b = atom_add_shared(counters + 4u * d0, 128u);
+                b = __shfl_sync(0xffffffffu, b, 0) + 4u * (uint32_t)lane;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) r[c] = b + c;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) r[c] = live[c] ? atom_add_shared(counters + 4u * d[c], 1u) : 0xffffffffu;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
                 if (sparse) {
-                    if (r < (uint32_t)CAP) st_shared(bins_base + 4u * (d * (uint32_t)CAP + r), key[v][c]);
+                    if (r[c] < (uint32_t)CAP) st_shared(bins_base + 4u * (d[c] * (uint32_t)CAP + r[c]), key[v][c]);
                 } else {
-                    if (live) st_shared(bins_base + 4u * r, key[v][c]);
+                    if (live[c]) st_shared(bins_base + 4u * r[c], key[v][c]);
                 }
             }
+        }
     };
+
+    // ---- a tile whose keys all share the digit (presorted / reversed input: every tile but the ones on bucket edges) is
+    //      copied straight from the registers, in input order, behind ONE cursor atomic ----
+    {
+        uint32_t k_or = key[0][0], k_and = key[0][0];
+#pragma unroll
+        for (int v = 0; v < VPT; ++v)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { k_or |= key[v][c]; k_and &= key[v][c]; }
+        const uint32_t mine = __byte_perm(k_or, 0u, prmt_sel);
+        const bool uniform = full && __byte_perm(k_or ^ k_and, 0u, prmt_sel) == 0;  // this thread's keys share the digit
+        if (tid == 0) s.overflow = mine;
+        __syncthreads();
+        const uint32_t dtile = s.overflow;
+        const int one_digit = __syncthreads_and(uniform && mine == dtile);
+        if (one_digit) {
+            if (tid == 0) s.cnt2[0] = atomicAdd(&cursor[dtile], (uint32_t)Cfg::TILE);
+            __syncthreads();
+            uint32_t* dst = out + s.cnt2[0];
+            if ((((uintptr_t)dst) & 15u) == 0) {
+#pragma unroll
+                for (int v = 0; v < VPT; ++v) reinterpret_cast<uint4*>(dst)[v * THREADS + tid] = make_uint4(key[v][0], key[v][1], key[v][2], key[v][3]);
+            } else {
+#pragma unroll
+                for (int v = 0; v < VPT; ++v)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dst[(v * THREADS + tid) * 4 + c] = key[v][c];
+            }
+            return;
+        }
+        if (tid == 0) s.overflow = 0;
+        // (the barrier after claim_all orders this store before the digit threads' stores to s.overflow)
+    }
     claim_all(cnt_base, true);
     __syncthreads();
 
@@ -341,37 +381,31 @@ msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out
     }
     __syncthreads();
     if (!s.overflow) {
-        // ---- sparse route: warp w copies bins w, w + WARPS, ... (two bins in flight); lane l of step k handles the key that
-        //      lands on word l of the k-th 128-byte line touched by the bin's run, so every store fills one aligned line ----
+        // ---- sparse route: warp w copies bins w, w + WARPS, ...; lane l of step k handles the key that lands on word l of
+        //      the k-th 128-byte line touched by the bin's run, so every store fills one aligned line.  Three steps cover
+        //      count + misalignment <= 96 (all but a few bins); a loop takes the rest ----
         const uint32_t out_word = (uint32_t)((uintptr_t)out >> 2);
-        for (int d = warp; d < RADIX; d += 2 * Cfg::WARPS) {
-            const int d1 = d + Cfg::WARPS;
-            const uint2 c0 = s.info[d];
-            const uint2 c1 = d1 < RADIX ? s.info[d1] : make_uint2(0u, 0u);
-            const uint32_t a0 = (out_word + c0.y) & 31u, a1 = (out_word + c1.y) & 31u;  // position of the run's first key inside its line
-            const uint32_t j0 = (uint32_t)lane - a0, j1 = (uint32_t)lane - a1;          // (wraps to a huge value where the line starts before the run)
-            const uint32_t* bin0 = &s.bins[d * CAP];
-            const uint32_t* bin1 = &s.bins[(d1 < RADIX ? d1 : d) * CAP];
-            uint32_t* dst0 = out + c0.y;
-            uint32_t* dst1 = out + c1.y;
-            // the first two lines of each run: all of it unless count + a > 64
-            const bool p00 = j0 < c0.x, p01 = j0 + 32u < c0.x, p10 = j1 < c1.x, p11 = j1 + 32u < c1.x;
-            uint32_t v00 = 0, v01 = 0, v10 = 0, v11 = 0;
-            if (p00) v00 = bin0[j0];
-            if (p01) v01 = bin0[j0 + 32u];
-            if (p10) v10 = bin1[j1];
-            if (p11) v11 = bin1[j1 + 32u];
-            if (p00) dst0[j0] = v00;
-            if (p01) dst0[j0 + 32u] = v01;
-            if (p10) dst1[j1] = v10;
-            if (p11) dst1[j1 + 32u] = v11;
-            for (uint32_t k32 = 64; k32 < c0.x + a0; k32 += 32) {  // warp-uniform trip counts
-                const uint32_t j = k32 + j0;
-                if (j < c0.x) dst0[j] = bin0[j];
-            }
-            for (uint32_t k32 = 64; k32 < c1.x + a1; k32 += 32) {
-                const uint32_t j = k32 + j1;
-                if (j < c1.x) dst1[j] = bin1[j];
+        auto lds = [](uint32_t addr) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; };
+        uint2 next = s.info[warp];
+        for (int d = warp; d < RADIX; d += Cfg::WARPS) {
+            const uint2 ci = next;
+            if (d + Cfg::WARPS < RADIX) next = s.info[d + Cfg::WARPS];  // the next bin's descriptor is in flight during this bin's copy
+            const uint32_t a = (out_word + ci.y) & 31u;         // position of the run's first key inside its line
+            const int32_t j0 = (int32_t)lane - (int32_t)a;        // negative where the line starts before the run
+            const uint32_t sbin = bins_base + 4u * (uint32_t)(d * CAP + j0);
+            uint32_t* dst = out + (uint32_t)((int32_t)ci.y + j0);  // (not dereferenced where j0 < 0)
+            const int32_t cnt_i = (int32_t)ci.x;
+            const bool p0 = j0 >= 0 && j0 < cnt_i, p1 = j0 + 32 < cnt_i, p2 = j0 + 64 < cnt_i;
+            uint32_t v0, v1, v2;
+            if (p0) v0 = lds(sbin);
+            if (p1) v1 = lds(sbin + 128u);
+            if (p2) v2 = lds(sbin + 256u);
+            if (p0) dst[0] = v0;
+            if (p1) dst[32] = v1;
+            if (p2) dst[64] = v2;
+            if (cnt_i + (int32_t)a > 96) {  // warp-uniform, rare
+                for (int32_t k32 = 96; k32 < cnt_i + (int32_t)a; k32 += 32)
+                    if (j0 + k32 < cnt_i) dst[k32] = lds(sbin + 4u * (uint32_t)k32);
             }
         }
         return;
@@ -394,35 +428,56 @@ msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out
 // =================================================================================================
 // F: every top-16 bucket sorted on its low 16 bits by counting, in shared memory, in place
 // =================================================================================================
-// Counters: 65 536 bins x 4 bits = 8 192 words (bin b: nibble b & 7 of word b >> 3).  Per key one ATOMS with return: the old
-// nibble is the key's rank among equal keys.  Scan: thread t adds up the nibbles of its 32 consecutive words, a block scan
-// makes that the exclusive prefix wp[] of every word.  Lookup: slot = wp[word] + (sum of the word's nibbles below mine) +
-// rank; the nibble sum is one multiply ((x * 0x11111111) >> 28 adds the eight nibbles when the sum is below 16).
-// Anything that would break the nibble arithmetic -- 16 or more equal keys, a word whose eight bins hold more than 15 keys
-// -- is caught exactly (old nibble == 15; word total > 15; and, for nibble wraps, the checksum of all words against the
-// bucket size) and sends the bucket to the robust route: a stable two-pass LSD sort in the same shared memory.
-// The words are stored XOR-swizzled inside each thread's 128-byte scan range so the scan's LDS.128 are conflict-free.
+// Counters: 65 536 values x 4 bits = 8 192 words (value v: nibble v & 7 of word v >> 3).  Per key one ATOMS with return: the
+// old nibble is the key's rank among equal keys.  Scan: thread t adds up the nibbles of its 32 consecutive words, a block
+// scan makes that the exclusive prefix wp[] of every word.  Lookup: slot = wp[word] + (sum of the word's nibbles below
+// mine) + rank; the nibble sum is one multiply ((x * 0x11111111) >> 28 adds the eight nibbles when the sum is below 16).
+// The low halves go to their slots in a 16-bit staging array (the high half is the bucket's number) and are written back
+// with whole-line stores.  Anything that would break the nibble arithmetic -- 16 or more equal keys, a word whose eight
+// values hold more than 15 keys -- is caught exactly (old nibble == 15; word total > 15; and, for nibble wraps, the checksum
+// of all words against the bucket size) and sends the bucket to the robust route: a stable two-pass LSD sort in the same
+// shared memory.  Counter words and wp[] are stored XOR-swizzled inside each thread's scan range so the scan's 128-bit
+// accesses are conflict-free.
+//
+// Measured and rejected (profiles/r2f_msd_perf.txt): writing the sorted bucket back FROM the counters (no ranks, no lookup,
+// no staging: lane l walks word 32 r + l of row r and peels its non-empty nibbles off with ffs) -- only 39 % of the lanes
+// have a non-empty word and a row of 32 words holds 16 keys, so the walk costs 300 warp instructions per 32 keys against
+// 27 for the lookup: 2.94 ms instead of 0.88 at 2^28.
 template <int THREADS, int IPT>
 struct MsdBucketConfig {
     static constexpr int CAP = THREADS * IPT;
     static constexpr int WORDS = (1 << MSD_LOW_BITS) / 8;
-    static constexpr int WORDS_PER_THREAD = WORDS / THREADS;
+    static constexpr int WORDS_PER_THREAD = WORDS / THREADS;  // 32 (256 threads) or 16 (512 threads)
+    static constexpr int CHUNKS = WORDS_PER_THREAD / 4;       // 16-byte chunks of counter words per thread
     struct Smem {
         alignas(16) uint32_t cnt[WORDS];
         alignas(16) uint16_t wp[WORDS];
-        alignas(16) uint32_t staged[CAP];
+        alignas(16) uint16_t staged[CAP + 64];  // low 16 bits of the keys in sorted order (the high 16 are the bucket's number) + dummy slots
         uint32_t warp_total[THREADS / 32];
-        uint32_t flags;
+        uint32_t dummy[32];                // keys outside the bucket aim here (bank = lane)
     };
     // the robust route needs two key buffers, the per-warp counters of the stable ranking and its scratch
     static constexpr size_t ROBUST_BYTES = 2 * (size_t)CAP * 4 + (size_t)(THREADS / 32) * RADIX * 4 + 64 * 4;
     static constexpr size_t SMEM_BYTES = sizeof(Smem) > ROBUST_BYTES ? sizeof(Smem) : ROBUST_BYTES;
 };
 
-// byte offset of counter word (key's low 16 bits >> 3), swizzled: chunk (16 B) index inside the 128-byte group ^= group & 7
+// Byte offset of counter word (key's low 16 bits >> 3), swizzled so that the scan's LDS.128 are conflict-free: thread t of
+// the scan owns CHUNKS consecutive 16-byte chunks, the eight threads of a quarter-warp would all hit the same bank group,
+// so chunk j of thread t is stored at chunk j ^ f(t) of the thread's own range (f(t) = t & 7 for 8 chunks per thread,
+// (t >> 1) & 3 for 4); both are bits 8.. of the key's low half.
+template <int CHUNKS>
 __device__ __forceinline__ uint32_t msd_word_offset(uint32_t key) {
-    const uint32_t plain = (key & 0xfff8u) >> 1;  // 4 * (bin >> 3)
-    return plain ^ ((key >> 4) & 0x70u);          // group = bin >> 8
+    static_assert(CHUNKS == 8 || CHUNKS == 4, "256 or 512 threads");
+    const uint32_t plain = (key & 0xfff8u) >> 1;  // 4 * (value >> 3)
+    return plain ^ ((key >> 4) & (CHUNKS == 8 ? 0x70u : 0x30u));
+}
+// Byte offset of wp[word] (u16): thread t of the scan owns CHUNKS / 2 consecutive 16-byte chunks of wp (8 words each);
+// chunk j of them is stored at j ^ g(t), g(t) = (t >> 1) & 3 for 4 chunks per thread (quarter-warps then cover all eight bank
+// groups), (t >> 2) & 1 for 2.
+template <int CHUNKS>
+__device__ __forceinline__ uint32_t msd_wp_offset(uint32_t key) {
+    const uint32_t plain = (key & 0xfff8u) >> 2;  // 2 * (value >> 3)
+    return plain ^ (CHUNKS == 8 ? ((key >> 5) & 0x30u) : ((key >> 5) & 0x10u));
 }
 
 template <int THREADS>
@@ -430,27 +485,41 @@ __device__ void msd_bucket_robust(unsigned char* smem, uint32_t* __restrict__ da
 
 template <int THREADS, int IPT, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
-msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ bucket_off, uint32_t minus_one) {
+msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ bucket_off, uint32_t minus_one, uint32_t pf_buckets) {
     using Cfg = MsdBucketConfig<THREADS, IPT>;
-    static_assert(Cfg::WORDS_PER_THREAD == 32, "the scan gives every thread one 128-byte group of counter words");
+    constexpr int CHUNKS = Cfg::CHUNKS;
     extern __shared__ __align__(16) unsigned char msd_smem_raw[];
     typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(msd_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t start = bucket_off[blockIdx.x];
     const uint32_t size = bucket_off[blockIdx.x + 1] - start;
+    // the CTA that will take over this CTA's slot handles a bucket about pf_buckets further on: pull it into L2 now
+    if (tid == 32 && pf_buckets && blockIdx.x + pf_buckets < (uint32_t)MSD_BUCKETS) {
+        const uint32_t p0 = bucket_off[blockIdx.x + pf_buckets] & ~3u, p1 = (bucket_off[blockIdx.x + pf_buckets + 1] + 3u) & ~3u;
+        if (p1 > p0 && (((uintptr_t)data & 15u) == 0)) bulk_prefetch_l2(data + p0, (p1 - p0) * 4u);
+    }
     if (size <= 1) return;
-    uint32_t* __restrict__ keys = data + start;
+    // The bucket is addressed through the 128-byte aligned window that starts `lead` keys before it: slot e of the window
+    // (thread e % THREADS, item e / THREADS) holds key e - lead, so every warp-wide load and store covers whole lines.
+    const uint32_t lead = (uint32_t)(((uintptr_t)(data + start) >> 2) & 31u);
+    uint32_t* __restrict__ keys = data + start;           // (robust route)
+    uint32_t* __restrict__ window = data + start - lead;  // (never dereferenced below data + start)
 
     {   // zero the counters
         uint4* z = reinterpret_cast<uint4*>(s.cnt);
 #pragma unroll
         for (int i = 0; i < Cfg::WORDS / 4 / THREADS; ++i) z[i * THREADS + tid] = make_uint4(0, 0, 0, 0);
-        if (tid == 0) s.flags = 0;
     }
+    // this thread holds window slots tid, tid + THREADS, ...: the first `mine_n` of its IPT items, minus item 0 when
+    // tid < lead
+    const uint32_t wend = lead + size;
+    const int mine_n = wend > (uint32_t)tid ? (int)((wend - (uint32_t)tid + THREADS - 1) / THREADS) : 0;
+    const bool skip0 = (uint32_t)tid < lead;
+    auto is_valid = [&](int i) { return i < mine_n && !(i == 0 && skip0); };
     uint32_t key[IPT];
 #pragma unroll
-    for (int i = 0; i < IPT; ++i)
-        if ((uint32_t)(i * THREADS + tid) < size) key[i] = keys[i * THREADS + tid];
+    for (int i = 0; i < IPT; ++i) key[i] = is_valid(i) ? window[i * THREADS + tid] : 0u;
+    if (tid < 32) s.dummy[tid] = 0;
     __syncthreads();
 
     // ---- count; the returned nibble is the rank among equal keys ----
@@ -458,30 +527,51 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
     uint32_t ranks[(IPT + 7) / 8];
 #pragma unroll
     for (int i = 0; i < (IPT + 7) / 8; ++i) ranks[i] = 0;
-    uint32_t bad = 0;
+    // Keys outside the bucket (the first or the last one or two of a thread) take part with a zero increment on a private
+    // dummy word: no branch per key.
+    uint32_t worst = 0;  // largest old nibble seen: 15 means the nibble wrapped (the 16th equal key)
+    const uint32_t dummy_addr = smem_addr(&s.dummy[lane]);
+    constexpr int BATCH = 6;  // atomics in flight per thread before their results are used
 #pragma unroll
-    for (int i = 0; i < IPT; ++i)
-        if ((uint32_t)(i * THREADS + tid) < size) {
-            const uint32_t sh = (key[i] & 7u) << 2;
-            const uint32_t old = atom_add_shared(cnt_base + msd_word_offset(key[i]), 1u << sh);
-            const uint32_t r = (old >> sh) & 15u;
-            bad |= (r == 15u) ? 1u : 0u;  // the 16th equal key: the nibble wrapped
-            ranks[i >> 3] |= r << (4 * (i & 7));
+    for (int i0 = 0; i0 < IPT; i0 += BATCH) {
+        uint32_t old[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int i = i0 + j;
+            if (i < IPT) {
+                const bool valid = is_valid(i);
+                old[j] = atom_add_shared(valid ? cnt_base + msd_word_offset<CHUNKS>(key[i]) : dummy_addr, valid ? 1u << ((key[i] & 7u) << 2) : 0u);
+            }
         }
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int i = i0 + j;
+            if (i < IPT) {
+                const uint32_t r = (old[j] >> ((key[i] & 7u) << 2)) & 15u;  // (dummy word: always 0)
+                worst = max(worst, r);
+                ranks[i >> 3] |= r << (4 * (i & 7));
+            }
+        }
+    }
+    uint32_t bad = worst == 15u ? 1u : 0u;
     __syncthreads();
 
-    // ---- scan of the counter words: thread t owns words 32 t .. 32 t + 31 (chunk j of them sits at chunk j ^ (t & 7)) ----
+    // ---- scan of the counter words: thread t owns words WPT t .. WPT t + WPT - 1 ----
     uint32_t total = 0;
     {
-        const uint4* mine = reinterpret_cast<const uint4*>(s.cnt) + tid * 8;
-        uint4* wp4 = reinterpret_cast<uint4*>(s.wp) + tid * 4;  // wp[] of my 32 words, two per register (not swizzled)
+        const uint4* mine = reinterpret_cast<const uint4*>(s.cnt) + tid * CHUNKS;
+        // wp[] of my words, two per register; my CHUNKS / 2 16-byte chunks are swizzled among themselves like the counters
+        // (msd_wp_offset), so that neither these stores nor the base update below conflict
+        uint4* wp4 = reinterpret_cast<uint4*>(s.wp) + tid * (CHUNKS / 2);
+        const int swz = CHUNKS == 8 ? (tid & 7) : ((tid >> 1) & 3);
+        const int wswz = CHUNKS == 8 ? ((tid >> 1) & 3) : ((tid >> 2) & 1);
         uint32_t run = 0, wide = 0;
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {  // eight words at a time: their prefixes (relative to my first word) fill one 16-byte store
+        for (int jj = 0; jj < CHUNKS / 2; ++jj) {  // eight words at a time: their prefixes (relative to my first word) fill one 16-byte store
             uint32_t pre[8];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const uint4 q = mine[(2 * jj + h) ^ (tid & 7)];
+                const uint4 q = mine[(2 * jj + h) ^ swz];
                 const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -489,10 +579,10 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
                     const uint32_t before = run;
                     run = __dp4a(w[k] & 0x0f0f0f0fu, 0x01010101u, run);
                     run = __dp4a((w[k] >> 4) & 0x0f0f0f0fu, 0x01010101u, run);
-                    wide |= (run - before) >> 4;  // a word whose eight bins hold 16 or more keys
+                    wide |= (run - before) >> 4;  // a word whose eight values hold 16 or more keys
                 }
             }
-            wp4[jj] = make_uint4(pre[0] | (pre[1] << 16), pre[2] | (pre[3] << 16), pre[4] | (pre[5] << 16), pre[6] | (pre[7] << 16));
+            wp4[jj ^ wswz] = make_uint4(pre[0] | (pre[1] << 16), pre[2] | (pre[3] << 16), pre[4] | (pre[5] << 16), pre[6] | (pre[7] << 16));
         }
         total = run;
         bad |= wide ? 1u : 0u;
@@ -516,10 +606,10 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
         base += inc - total;
         const uint32_t base2 = base | (base << 16);  // slots are below 2^16: the halves cannot carry into each other
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 o = wp4[j];
+        for (int j = 0; j < CHUNKS / 2; ++j) {
+            uint4 o = wp4[j ^ wswz];
             o.x += base2; o.y += base2; o.z += base2; o.w += base2;
-            wp4[j] = o;
+            wp4[j ^ wswz] = o;
         }
     }
     if (__syncthreads_or((int)bad)) {
@@ -528,22 +618,23 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
     }
 
     // ---- lookup: slot = wp[word] + nibbles of the word below mine + rank among equal keys ----
-    const uint32_t wp_base = smem_addr(&s.wp[0]), staged_base = smem_addr(&s.staged[0]);
+    const unsigned char* cnt_bytes = reinterpret_cast<const unsigned char*>(s.cnt);
+    const unsigned char* wp_bytes = reinterpret_cast<const unsigned char*>(s.wp);
 #pragma unroll
-    for (int i = 0; i < IPT; ++i)
-        if ((uint32_t)(i * THREADS + tid) < size) {
-            const uint32_t sh = (key[i] & 7u) << 2;
-            uint32_t word, wpv;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(cnt_base + msd_word_offset(key[i])));
-            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(wpv) : "r"(wp_base + ((key[i] & 0xfff8u) >> 2)));
-            const uint32_t below = word & ~(0xffffffffu << sh);
-            const uint32_t slot = wpv + ((below * 0x11111111u) >> 28) + ((ranks[i >> 3] >> (4 * (i & 7))) & 15u);
-            st_shared(staged_base + 4u * slot, key[i]);
-        }
+    for (int i = 0; i < IPT; ++i) {
+        const bool valid = is_valid(i);  // (a key outside the bucket reads the words of key 0 and stores to a dummy slot)
+        const uint32_t sh = (key[i] & 7u) << 2;
+        const uint32_t word = *reinterpret_cast<const uint32_t*>(cnt_bytes + msd_word_offset<CHUNKS>(key[i]));
+        const uint32_t wpv = *reinterpret_cast<const uint16_t*>(wp_bytes + msd_wp_offset<CHUNKS>(key[i]));
+        const uint32_t below = word & ~(0xffffffffu << sh);
+        const uint32_t slot = wpv + ((below * 0x11111111u) >> 28) + ((ranks[i >> 3] >> (4 * (i & 7))) & 15u);
+        s.staged[valid ? slot : (uint32_t)(Cfg::CAP + 2 * lane)] = (uint16_t)key[i];
+    }
     __syncthreads();
+    const uint32_t high = blockIdx.x << MSD_LOW_BITS;
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
-        if ((uint32_t)(i * THREADS + tid) < size) keys[i * THREADS + tid] = s.staged[i * THREADS + tid];
+        if (is_valid(i)) window[i * THREADS + tid] = high | s.staged[i * THREADS + tid - lead];
 }
 
 // Robust route of F: stable LSD sort of the bucket on its low 16 bits, two 8-bit passes between two shared-memory buffers,

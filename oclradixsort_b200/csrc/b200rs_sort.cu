@@ -873,7 +873,7 @@ struct SortPlan {
 
 // The MSD path is tried for full 32-bit key sorts of this size range (below: per-bucket fixed costs of the counting step
 // dominate; above: a uniform input's buckets exceed its shared memory and element indices are kept in 32 bits).
-constexpr uint64_t MSD_MIN_N = 1ull << 40 /* automatic selection off until the path wins (first measurement: 2.96 ms vs 2.85 at 2^28) */, MSD_MAX_N = (1ull << 30) - 1;
+constexpr uint64_t MSD_MIN_N = 3ull << 26 /* measured: 2^27 keys 1.50 ms either way, 2^28 2.19 (MSD) against 2.85 (LSD) */, MSD_MAX_N = (1ull << 30) - 1;
 constexpr uint32_t MSD_MIN_P_TILE = 4096;  // smallest partition tile among the compiled shapes: the tile table is sized for it
 enum MsdMode { MSD_AUTO = 0, MSD_FORCED = 1 };  // MSD_FORCED: b200rs_sort_keys_u32_msd -- no lower size limit
 template <typename ElemT>
@@ -908,7 +908,7 @@ int make_plan(uint64_t n, int sort_bits, SortPlan* p, int msd_mode = MSD_AUTO) {
         p->msd_ctl_off = off;        off += 256;
         p->msd_bucket_off_off = off; off += b200rs_align_up((size_t)(MSD_BUCKETS + 1) * sizeof(uint32_t), 256);
         p->msd_cursor2_off = off;    off += (size_t)MSD_BUCKETS * sizeof(uint32_t);
-        p->msd_cursor1_off = off;    off += b200rs_align_up((size_t)RADIX * sizeof(uint32_t), 256);
+        p->msd_cursor1_off = off;    off += b200rs_align_up((size_t)2 * RADIX * sizeof(uint32_t), 256);  // cursor1[256] | hist3[256]
         p->msd_tiles_off = off;      off += b200rs_align_up(((size_t)(n / MSD_MIN_P_TILE) + RADIX + 1) * sizeof(MsdTile), 256);
     }
     p->total_bytes = off ? off : 256;
@@ -936,7 +936,7 @@ struct MsdBucketShape {
     MsdBucketShape{(const void*)msd_bucket_kernel<THREADS, IPT, MIN_CTAS>, THREADS, THREADS * IPT, MsdBucketConfig<THREADS, IPT>::SMEM_BYTES, #THREADS "x" #IPT "/" #MIN_CTAS}
 
 inline const MsdPartitionShape& msd_partition_shape() {
-    static const MsdPartitionShape production = B200RS_MSD_P(256, 8, 64, 3);
+    static const MsdPartitionShape production = B200RS_MSD_P(512, 6, 80, 2);  // 12288-key tiles, 80 KiB of bins, 2 CTAs/SM (first sweep: profiles/r2a_msd_first_shapes.txt)
 #ifdef B200RS_EXPERIMENTS
     static const MsdPartitionShape v[] = {
         B200RS_MSD_P(256, 8, 64, 3),   // 0: 8192-key tiles, 64 KiB of bins
@@ -947,8 +947,13 @@ inline const MsdPartitionShape& msd_partition_shape() {
         B200RS_MSD_P(256, 4, 40, 5),   // 5: 4096-key tiles, 40 KiB
         B200RS_MSD_P(1024, 4, 112, 1), // 6: 16384-key tiles, one CTA per SM
         B200RS_MSD_P(512, 6, 80, 2),   // 7: 12288-key tiles
+        B200RS_MSD_P(512, 8, 96, 2),   // 8: 16384-key tiles, 96 KiB
+        B200RS_MSD_P(512, 5, 72, 3),   // 9: 10240-key tiles, 72 KiB
+        B200RS_MSD_P(768, 4, 80, 2),   // 10: 12288-key tiles, 768 threads
+        B200RS_MSD_P(1024, 3, 80, 2),  // 11: 12288-key tiles, 1024 threads
+        B200RS_MSD_P(640, 5, 80, 2),   // 12: 12800-key tiles
     };
-    const int idx = b200rs_exp_env("B200RS_MSD_P", 0);
+    const int idx = b200rs_exp_env("B200RS_MSD_P", 7);
     if (idx >= 0 && idx < (int)(sizeof(v) / sizeof(v[0]))) return v[idx];
 #endif
     return production;
@@ -956,21 +961,23 @@ inline const MsdPartitionShape& msd_partition_shape() {
 // the counting step keeps a whole bucket in registers + shared memory: the smallest shape that holds the largest bucket
 inline const MsdBucketShape* msd_bucket_shape(uint32_t max_bucket) {
     static const MsdBucketShape v[] = {
-        B200RS_MSD_F(256, 24, 3),  // 6144 keys, 72 KiB
-        B200RS_MSD_F(256, 36, 2),  // 9216 keys, 84 KiB
-        B200RS_MSD_F(256, 48, 2),  // 12288 keys, 96 KiB
+        B200RS_MSD_F(256, 18, 3),  // 4608 keys
+        B200RS_MSD_F(256, 24, 3),  // 6144 keys
+        B200RS_MSD_F(256, 36, 2),  // 9216 keys
+        B200RS_MSD_F(256, 48, 2),  // 12288 keys
     };
 #ifdef B200RS_EXPERIMENTS
-    static const MsdBucketShape x[] = {B200RS_MSD_F(256, 20, 3), B200RS_MSD_F(256, 32, 2), B200RS_MSD_F(256, 28, 3)};
+    static const MsdBucketShape x[] = {B200RS_MSD_F(512, 9, 3), B200RS_MSD_F(512, 10, 3), B200RS_MSD_F(512, 12, 2), B200RS_MSD_F(256, 18, 4), B200RS_MSD_F(256, 20, 3),
+                                       B200RS_MSD_F(512, 9, 2)};
     const int idx = b200rs_exp_env("B200RS_MSD_F", -1);
-    if (idx >= 3 && idx < 6 && max_bucket <= (uint32_t)x[idx - 3].cap) return &x[idx - 3];
-    if (idx >= 0 && idx < 3 && max_bucket <= (uint32_t)v[idx].cap) return &v[idx];
+    if (idx >= 4 && idx < 10 && max_bucket + 31u <= (uint32_t)x[idx - 4].cap) return &x[idx - 4];
+    if (idx >= 0 && idx < 4 && max_bucket + 31u <= (uint32_t)v[idx].cap) return &v[idx];
 #endif
     for (const MsdBucketShape& f : v)
-        if (max_bucket <= (uint32_t)f.cap) return &f;
+        if (max_bucket + 31u <= (uint32_t)f.cap) return &f;  // (+31: the bucket is read through a 128-byte aligned window)
     return nullptr;
 }
-constexpr uint32_t MSD_MAX_BUCKET = 256 * 48;
+constexpr uint32_t MSD_MAX_BUCKET = 256 * 48 - 31;
 
 // Returns B200RS_OK when the keys were sorted here, MSD_NOT_ELIGIBLE when the input is not eligible (the caller runs the LSD
 // path), an error code otherwise.  ONE host round trip: the choice between the two paths depends on the joint histogram, and both
@@ -996,11 +1003,13 @@ int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, c
         const uint64_t per_block = (uint64_t)MSD_HIST_THREADS * MSD_HIST_VECS * 4;
         uint64_t blocks = (n + per_block - 1) / per_block;
         if (blocks > (uint64_t)dev->num_sms) blocks = (uint64_t)dev->num_sms;
-        msd_hist16_kernel<<<(unsigned)blocks, MSD_HIST_THREADS, MSD_HIST_SMEM, dev->stream>>>(inout, n, reinterpret_cast<unsigned long long*>(joint), ctl);
+        msd_hist16_kernel<<<(unsigned)blocks, MSD_HIST_THREADS, MSD_HIST_SMEM, dev->stream>>>(inout, n, reinterpret_cast<unsigned long long*>(joint), ctl, MSD_MAX_BUCKET);
     }
     {
+        uint32_t* hist3 = cursor1 + RADIX;
         b200rs_launch_scope scope(dev, "msd_plan", MSD_BUCKETS, (uint64_t)MSD_BUCKETS * 12);
-        msd_plan_kernel<<<1, MSD_PLAN_THREADS, 0, dev->stream>>>(joint, n32, (uint32_t)ps.tile, MSD_MAX_BUCKET, bucket_off, cursor2, cursor1, tiles, ctl);
+        msd_plan_sums_kernel<<<RADIX, RADIX, 0, dev->stream>>>(joint, hist3, ctl);
+        msd_plan_kernel<<<RADIX, RADIX, 0, dev->stream>>>(joint, hist3, n32, (uint32_t)ps.tile, MSD_MAX_BUCKET, bucket_off, cursor2, cursor1, tiles, ctl);
     }
     B200RS_CUDA(cudaGetLastError());
     B200RS_CUDA(cudaMemcpyAsync(dev->pinned_word, ctl, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, dev->stream));
@@ -1008,10 +1017,10 @@ int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, c
     if (dev->pinned_word[MSD_CTL_INELIGIBLE]) return MSD_NOT_ELIGIBLE;
     const MsdBucketShape* fs = msd_bucket_shape(dev->pinned_word[MSD_CTL_MAX_BUCKET]);
     if (!fs) return MSD_NOT_ELIGIBLE;
+    B200RS_TRY(b200rs_kernel_setup(dev, fs->kernel, fs->smem));
 
     B200RS_TRY(b200rs_kernel_setup(dev, ps.p1, ps.smem));
     B200RS_TRY(b200rs_kernel_setup(dev, ps.p2, ps.smem));
-    B200RS_TRY(b200rs_kernel_setup(dev, fs->kernel, fs->smem));
     const uint32_t* in1 = inout;
     const MsdTile* no_tiles = nullptr;
     int shift1 = 24, shift2 = 16;
@@ -1031,8 +1040,10 @@ int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, c
     {
         b200rs_launch_scope scope(dev, "msd_bucket_keys", n, 8ull * n);
         const uint32_t* off_c = bucket_off;
+        // L2 prefetch distance in buckets: about twice the number of co-resident CTAs
+        uint32_t pf_buckets = (uint32_t)b200rs_exp_env("B200RS_MSD_PF", dev->num_sms * 6);
         uint32_t minus_one = 0xffffffffu;
-        void* args[] = {&inout, &off_c, &minus_one};
+        void* args[] = {&inout, &off_c, &minus_one, &pf_buckets};
         B200RS_CUDA(cudaLaunchKernel(fs->kernel, dim3(MSD_BUCKETS), dim3(fs->threads), args, fs->smem, dev->stream));
     }
     B200RS_CUDA(cudaGetLastError());
