@@ -62,7 +62,7 @@ constexpr size_t MSD_HIST_SMEM = (size_t)(MSD_BUCKETS / 2) * sizeof(uint32_t);
 // that hit the same counter are serialised -- and would be sent to the LSD path anyway).  The decision is local: the
 // CTAs see statistically the same data (grid-stride rounds), so they all stop within a check or two of each other,
 // and nobody waits for a global flag.
-constexpr int MSD_HIST_CHECK_ROUNDS = 16;  // 256 Ki keys per CTA between checks
+constexpr int MSD_HIST_FIRST_CHECK = 8, MSD_HIST_CHECK_ROUNDS = 64;  // rounds (16 Ki keys per CTA each): one early look, then one per 1 Mi keys
 __global__ void __launch_bounds__(MSD_HIST_THREADS, 1)
 msd_hist16_kernel(const uint32_t* __restrict__ in, uint64_t n, unsigned long long* __restrict__ joint2 /*[32768] pairs of u32 counters*/,
                   uint32_t* __restrict__ ctl, uint32_t bucket_cap) {
@@ -105,24 +105,16 @@ msd_hist16_kernel(const uint32_t* __restrict__ in, uint64_t n, unsigned long lon
                 counted += 4;
             }
         }
-        if (++rounds % MSD_HIST_CHECK_ROUNDS == 0) {  // (every thread of the CTA runs the same number of rounds)
-            __syncthreads();
-            uint32_t over = 0, seen_now = 0;
+        ++rounds;
+        if (rounds == MSD_HIST_FIRST_CHECK || rounds % MSD_HIST_CHECK_ROUNDS == 0) {  // (every thread of the CTA runs the same number of rounds)
+            // a heuristic look at the table (no barrier in front: reductions still in flight only make it a little stale);
+            // counters that wrapped in between are caught by the checksum at the end
+            uint32_t over = 0;
             for (int w = tid; w < MSD_BUCKETS / 2; w += MSD_HIST_THREADS) {
                 const uint32_t x = msd_tab[w];
-                seen_now += (x & 0xffffu) + (x >> 16);
                 over |= ((x & 0xffffu) > bucket_cap || (x >> 16) > bucket_cap) ? 1u : 0u;
             }
-            // a counter that wrapped since the last check (extreme skew) shows up as a checksum mismatch, as at the end
-            uint32_t dd = seen_now - counted;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
-            if (lane == 0) s_sum[tid >> 5] = dd;
-            __syncthreads();
-            uint32_t tot = 0;
-#pragma unroll
-            for (int w = 0; w < MSD_HIST_THREADS / 32; ++w) tot += s_sum[w];
-            if (__syncthreads_or((int)(over | (tot != 0u)))) {  // the histogram is abandoned: nobody will use it
+            if (__syncthreads_or((int)over)) {  // the histogram is abandoned: nobody will use it
                 if (tid == 0) atomicOr(&ctl[MSD_CTL_INELIGIBLE], (uint32_t)MSD_WHY_EARLY);
                 return;
             }
@@ -257,7 +249,7 @@ template <int THREADS, int VPT, int CAP, int MIN_CTAS, bool SEGMENTED>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, int shift,
                      uint32_t* __restrict__ cursor /* P1: [256]; P2: [65536], bucket b's 256 cursors at 256 b */,
-                     const MsdTile* __restrict__ tiles, const uint32_t* __restrict__ ctl) {
+                     const MsdTile* __restrict__ tiles, const uint32_t* __restrict__ ctl, uint32_t pf_tiles /* L2 prefetch distance, 0 = off */) {
     using Cfg = MsdPartitionConfig<THREADS, VPT, CAP>;
     static_assert(THREADS >= RADIX, "one thread per digit");
     extern __shared__ __align__(16) unsigned char msd_smem_raw[];
@@ -266,14 +258,25 @@ msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out
 
     uint32_t start, count;
     if (SEGMENTED) {
-        if (blockIdx.x >= ctl[MSD_CTL_P2_TILES]) return;  // the grid was sized for the upper bound n / TILE + 256
+        const uint32_t num_tiles = ctl[MSD_CTL_P2_TILES];
+        if (blockIdx.x >= num_tiles) return;  // the grid was sized for the upper bound n / TILE + 256
         const MsdTile t = tiles[blockIdx.x];
         start = t.start;
         count = t.meta & 0xffffu;
         cursor += (size_t)(t.meta >> 16) * RADIX;
+        // the tile a CTA will load about one wave of CTAs from now is pulled into L2 (one bulk prefetch, nobody waits for it)
+        if (tid == 32 && pf_tiles && blockIdx.x + pf_tiles < num_tiles) {
+            const MsdTile p = tiles[blockIdx.x + pf_tiles];
+            const uint32_t bytes = (((p.meta & 0xffffu) + 3u) & ~3u) * 4u;
+            bulk_prefetch_l2(in + p.start, bytes);
+        }
     } else {
         start = blockIdx.x * (uint32_t)Cfg::TILE;
         count = min((uint32_t)Cfg::TILE, n - start);
+        if (tid == 32 && pf_tiles) {
+            const uint64_t p = ((uint64_t)blockIdx.x + pf_tiles) * Cfg::TILE;
+            if (p + Cfg::TILE <= n) bulk_prefetch_l2(in + p, (uint32_t)Cfg::TILE * 4u);
+        }
     }
     for (int i = tid; i < RADIX; i += THREADS) s.cnt[i] = 0;
     if (tid == 0) s.overflow = 0;
@@ -304,6 +307,7 @@ msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out
     const uint32_t cnt_base = smem_addr(&s.cnt[0]), bins_base = smem_addr(&s.bins[0]);
     const uint32_t prmt_sel = 0x4440u | (uint32_t)(shift >> 3);
     auto claim_all = [&](uint32_t counters, bool sparse) {
+        bool try_same = true;  // warp-uniform: the test is dropped once a vector fails it (random keys never pass; presorted ones always do)
 #pragma unroll
         for (int v = 0; v < VPT; ++v) {
             uint32_t d[4], r[4];
@@ -313,9 +317,13 @@ msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out
                 live[c] = full || (uint32_t)(v * THREADS + tid) * 4 + c < count;
                 d[c] = __byte_perm(key[v][c], 0u, prmt_sel);
             }
-            const uint32_t d0 = __shfl_sync(0xffffffffu, d[0], 0);
-            const bool same = live[3] && ((d[0] ^ d0) | (d[1] ^ d0) | (d[2] ^ d0) | (d[3] ^ d0)) == 0;  // (live[3] implies live[0..2])
-            if (__all_sync(0xffffffffu, same)) {
+            uint32_t d0 = 0;
+            if (try_same) {
+                d0 = __shfl_sync(0xffffffffu, d[0], 0);
+                const bool same = live[3] && ((d[0] ^ d0) | (d[1] ^ d0) | (d[2] ^ d0) | (d[3] ^ d0)) == 0;  // (live[3] implies live[0..2])
+                try_same = __all_sync(0xffffffffu, same);
+            }
+            if (try_same) {
                 uint32_t b = 0;
                 if (lane == 0) b = atom_add_shared(counters + 4u * d0, 128u);
                 b = __shfl_sync(0xffffffffu, b, 0) + 4u * (uint32_t)lane;
@@ -515,11 +523,11 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
     const uint32_t wend = lead + size;
     const int mine_n = wend > (uint32_t)tid ? (int)((wend - (uint32_t)tid + THREADS - 1) / THREADS) : 0;
     const bool skip0 = (uint32_t)tid < lead;
+    const int cta_n = (int)((wend + THREADS - 1) / THREADS);  // items any thread of the CTA holds (uniform): the rest is skipped outright
     auto is_valid = [&](int i) { return i < mine_n && !(i == 0 && skip0); };
     uint32_t key[IPT];
 #pragma unroll
     for (int i = 0; i < IPT; ++i) key[i] = is_valid(i) ? window[i * THREADS + tid] : 0u;
-    if (tid < 32) s.dummy[tid] = 0;
     __syncthreads();
 
     // ---- count; the returned nibble is the rank among equal keys ----
@@ -527,10 +535,8 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
     uint32_t ranks[(IPT + 7) / 8];
 #pragma unroll
     for (int i = 0; i < (IPT + 7) / 8; ++i) ranks[i] = 0;
-    // Keys outside the bucket (the first or the last one or two of a thread) take part with a zero increment on a private
-    // dummy word: no branch per key.
+    // Keys outside the bucket (the first or the last one or two of a thread): the atomic is predicated off, no branch per key.
     uint32_t worst = 0;  // largest old nibble seen: 15 means the nibble wrapped (the 16th equal key)
-    const uint32_t dummy_addr = smem_addr(&s.dummy[lane]);
     constexpr int BATCH = 6;  // atomics in flight per thread before their results are used
 #pragma unroll
     for (int i0 = 0; i0 < IPT; i0 += BATCH) {
@@ -538,16 +544,14 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) {
             const int i = i0 + j;
-            if (i < IPT) {
-                const bool valid = is_valid(i);
-                old[j] = atom_add_shared(valid ? cnt_base + msd_word_offset<CHUNKS>(key[i]) : dummy_addr, valid ? 1u << ((key[i] & 7u) << 2) : 0u);
-            }
+            old[j] = 0;
+            if (i < IPT && i < cta_n) old[j] = atom_add_shared_if(is_valid(i), cnt_base + msd_word_offset<CHUNKS>(key[i]), 1u << ((key[i] & 7u) << 2));  // 0 where not valid
         }
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) {
             const int i = i0 + j;
-            if (i < IPT) {
-                const uint32_t r = (old[j] >> ((key[i] & 7u) << 2)) & 15u;  // (dummy word: always 0)
+            if (i < IPT && i < cta_n) {
+                const uint32_t r = (old[j] >> ((key[i] & 7u) << 2)) & 15u;  // (not valid: 0)
                 worst = max(worst, r);
                 ranks[i >> 3] |= r << (4 * (i & 7));
             }
@@ -576,16 +580,15 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     pre[h * 4 + k] = run;
-                    const uint32_t before = run;
-                    run = __dp4a(w[k] & 0x0f0f0f0fu, 0x01010101u, run);
-                    run = __dp4a((w[k] >> 4) & 0x0f0f0f0fu, 0x01010101u, run);
-                    wide |= (run - before) >> 4;  // a word whose eight values hold 16 or more keys
+                    const uint32_t t = __dp4a(w[k] & 0x0f0f0f0fu, 0x01010101u, __dp4a((w[k] >> 4) & 0x0f0f0f0fu, 0x01010101u, 0u));
+                    run += t;
+                    wide |= t;  // bits 4.. set: a word whose eight values hold 16 or more keys
                 }
             }
             wp4[jj ^ wswz] = make_uint4(pre[0] | (pre[1] << 16), pre[2] | (pre[3] << 16), pre[4] | (pre[5] << 16), pre[6] | (pre[7] << 16));
         }
         total = run;
-        bad |= wide ? 1u : 0u;
+        bad |= (wide >> 4) ? 1u : 0u;
         // block-wide exclusive scan of the threads' totals
         uint32_t inc = total;
 #pragma unroll
@@ -622,6 +625,7 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
     const unsigned char* wp_bytes = reinterpret_cast<const unsigned char*>(s.wp);
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
+        if (i >= cta_n) break;  // uniform
         const bool valid = is_valid(i);  // (a key outside the bucket reads the words of key 0 and stores to a dummy slot)
         const uint32_t sh = (key[i] & 7u) << 2;
         const uint32_t word = *reinterpret_cast<const uint32_t*>(cnt_bytes + msd_word_offset<CHUNKS>(key[i]));

@@ -1022,19 +1022,21 @@ int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, c
     B200RS_TRY(b200rs_kernel_setup(dev, ps.p1, ps.smem));
     B200RS_TRY(b200rs_kernel_setup(dev, ps.p2, ps.smem));
     const uint32_t* in1 = inout;
+    // L2 prefetch distance of the partition passes in tiles: about one wave of co-resident CTAs
+    uint32_t pf_tiles = (uint32_t)b200rs_exp_env("B200RS_MSD_PPF", dev->num_sms * 2);
     const MsdTile* no_tiles = nullptr;
     int shift1 = 24, shift2 = 16;
     const uint32_t* ctl_c = ctl;
     {
         b200rs_launch_scope scope(dev, "msd_partition_keys_pass0", n, 8ull * n);
-        void* args[] = {&in1, &alt, (void*)&n32, &shift1, &cursor1, &no_tiles, &ctl_c};
+        void* args[] = {&in1, &alt, (void*)&n32, &shift1, &cursor1, &no_tiles, &ctl_c, &pf_tiles};
         B200RS_CUDA(cudaLaunchKernel(ps.p1, dim3((unsigned)((n + ps.tile - 1) / ps.tile)), dim3(ps.threads), args, ps.smem, dev->stream));
     }
     {
         b200rs_launch_scope scope(dev, "msd_partition_keys_pass1", n, 8ull * n);
         const uint32_t* in2 = alt;
         const MsdTile* tiles_c = tiles;
-        void* args[] = {&in2, &inout, (void*)&n32, &shift2, &cursor2, &tiles_c, &ctl_c};
+        void* args[] = {&in2, &inout, (void*)&n32, &shift2, &cursor2, &tiles_c, &ctl_c, &pf_tiles};
         B200RS_CUDA(cudaLaunchKernel(ps.p2, dim3((unsigned)(n / ps.tile + RADIX)), dim3(ps.threads), args, ps.smem, dev->stream));
     }
     {
