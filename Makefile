@@ -84,3 +84,11 @@ tools/_build/prims_dropin: tests/cpp/prims_dropin.cpp $(CSRC)/Pprims.cpp $(LIB) 
 	$(CXX) -std=c++11 -O2 -Wall -DNDEBUG -Iinclude tests/cpp/prims_dropin.cpp $(CSRC)/Pprims.cpp \
 	    -Loclradixsort_b200 -lb200rs -Wl,-rpath,'$$ORIGIN/../../oclradixsort_b200' -o $@
 .PHONY: prims_test
+
+# C++ caller of the partitioned sort: one process, one host thread per GPU (needs >= 2 GPUs to do anything); run by tests/test_gpu_dist.py
+dist_test: tools/_build/dist_dropin
+tools/_build/dist_dropin: tests/cpp/dist_dropin.cpp $(CSRC)/Pprims.cpp $(LIB) $(wildcard include/Adl/*.h include/Tahoe/*/*.h include/Tahoe/*/*/*.h)
+	mkdir -p tools/_build
+	$(CXX) -std=c++11 -O2 -Wall -DNDEBUG -Iinclude tests/cpp/dist_dropin.cpp $(CSRC)/Pprims.cpp \
+	    -Loclradixsort_b200 -lb200rs -lpthread -Wl,-rpath,'$$ORIGIN/../../oclradixsort_b200' -o $@
+.PHONY: dist_test

@@ -47,8 +47,8 @@ struct BufferBase {
     enum BufferType {
         BUFFER,
         BUFFER_CONST, BUFFER_STAGING, BUFFER_APPEND, BUFFER_RAW, BUFFER_W_COUNTER, BUFFER_INDEX, BUFFER_VERTEX,  // DX11 kinds, unused
-        BUFFER_ZERO_COPY,  // accepted and allocated like BUFFER: the CL backend's CL_MEM_ALLOC_HOST_PTR (AdlCL.inl:381-382) would be host memory
-                           // behind PCIe here, i.e. a sort at ~50 GB/s; getHostPtr / returnHostPtr go through the pinned staging block instead
+        BUFFER_ZERO_COPY,  // CL_MEM_ALLOC_HOST_PTR of the CL backend (AdlCL.inl:381-382): PINNED HOST memory the GPU reads and writes in place
+                           // over the host link (same pointer on both sides, unified addressing); getHostPtr returns it without a copy
     };
 };
 
@@ -89,7 +89,9 @@ struct Device {
 
     explicit Device(DeviceType type)
         : m_type(type), m_procType(Config::DEVICE_GPU), m_memoryUsage(0), m_interopAvailable(false), m_enableProfiling(false),
-          m_binaryFileVersion(0), m_handle(0), m_stage(0), m_stageBytes(0), m_stageBusy(false) {}
+          m_binaryFileVersion(0), m_handle(0) {
+        for (int i = 0; i < NUM_STAGES; ++i) { m_stages[i].p = 0; m_stages[i].bytes = 0; m_stages[i].event = 0; m_stages[i].mapped = false; m_stages[i].inFlight = false; }
+    }
     virtual ~Device() {}
 
     virtual void* getContext() const { return m_handle; }
@@ -101,9 +103,12 @@ struct Device {
         m_procType = Config::DEVICE_GPU;
     }
     virtual void release() {
-        if (m_stage) b200rs_host_free(m_handle, m_stage);
-        m_stage = 0;
-        m_stageBytes = 0;
+        if (m_handle) b200rs_device_sync(m_handle);  // copies out of the stages may still be in flight
+        for (int i = 0; i < NUM_STAGES; ++i) {
+            if (m_stages[i].p) b200rs_host_free(m_handle, m_stages[i].p);
+            if (m_stages[i].event) b200rs_event_destroy(m_handle, m_stages[i].event);
+            m_stages[i].p = 0; m_stages[i].bytes = 0; m_stages[i].event = 0; m_stages[i].mapped = false; m_stages[i].inFlight = false;
+        }
         if (m_handle) adlCheck(b200rs_device_destroy(m_handle), "b200rs_device_destroy");
         m_handle = 0;
     }
@@ -162,29 +167,61 @@ struct Device {
     Config::DeviceType getProcType() const { return m_procType; }
     b200rs_device* getHandle() const { return m_handle; }
 
-    // Pinned staging for Buffer::getHostPtr: one grow-only block per device, reused from map to map
-    // (a second concurrent mapping gets its own block).
-    void* acquireStage(size_t bytes, bool* ownedByCaller) const {
-        if (!m_stageBusy) {
-            if (bytes > m_stageBytes) {
-                if (m_stage) b200rs_host_free(m_handle, m_stage);
-                m_stage = 0;
-                m_stageBytes = 0;
-                if (!adlCheck(b200rs_host_alloc(m_handle, bytes, &m_stage), "b200rs_host_alloc")) return 0;
-                m_stageBytes = bytes;
+    // Pinned staging for Buffer::getHostPtr / returnHostPtr: a ring of NUM_STAGES grow-only blocks per device.
+    //   map   (getHostPtr)    takes a block nobody holds; the device -> host copy into it is stream-ordered, the caller
+    //                         waits (DeviceUtils::waitForCompletion) before reading, as with the reference's non-blocking
+    //                         clEnqueueMapBuffer (AdlCL.inl:544-555)
+    //   unmap (returnHostPtr) enqueues the host -> device copy out of the block and RETURNS (non-blocking
+    //                         clEnqueueUnmapMemObject, AdlCL.inl:557-565): the block carries an event and is handed out
+    //                         again only after that event has passed, so the host never overwrites bytes a copy still reads
+    // A mapping that finds every block held by other live mappings gets a block of its own.
+    void* acquireStage(size_t bytes, int* slot) const {
+        int pick = -1;
+        for (int pass = 0; pass < 2 && pick < 0; ++pass)
+            for (int i = 0; i < NUM_STAGES && pick < 0; ++i) {
+                Stage& st = m_stages[i];
+                if (st.mapped) continue;
+                if (st.inFlight) {
+                    int done = 0;
+                    if (pass == 0) b200rs_event_query(m_handle, st.event, &done);
+                    else done = b200rs_event_synchronize(m_handle, st.event) == B200RS_OK;  // second pass: wait for the first block that is only in flight
+                    if (!done) continue;
+                    st.inFlight = false;
+                }
+                pick = i;
             }
-            m_stageBusy = true;
-            *ownedByCaller = false;
-            return m_stage;
+        if (pick < 0) {  // every block is mapped by somebody else
+            void* p = 0;
+            adlCheck(b200rs_host_alloc(m_handle, bytes, &p), "b200rs_host_alloc");
+            *slot = -1;
+            return p;
         }
-        void* p = 0;
-        adlCheck(b200rs_host_alloc(m_handle, bytes, &p), "b200rs_host_alloc");
-        *ownedByCaller = true;
-        return p;
+        Stage& st = m_stages[pick];
+        if (bytes > st.bytes) {
+            if (st.p) b200rs_host_free(m_handle, st.p);
+            st.p = 0;
+            st.bytes = 0;
+            if (!adlCheck(b200rs_host_alloc(m_handle, bytes, &st.p), "b200rs_host_alloc")) return 0;
+            st.bytes = bytes;
+        }
+        st.mapped = true;
+        *slot = pick;
+        return st.p;
     }
-    void releaseStage(void* p, bool ownedByCaller) const {
-        if (ownedByCaller) b200rs_host_free(m_handle, p);
-        else m_stageBusy = false;
+    // `copyEnqueued`: a stream-ordered copy that reads the block was just enqueued (unmap); the block is recycled after it
+    void releaseStage(void* p, int slot, bool copyEnqueued) const {
+        if (slot < 0) {  // a private block: nothing else can wait for it
+            if (copyEnqueued) waitForCompletion();
+            b200rs_host_free(m_handle, p);
+            return;
+        }
+        Stage& st = m_stages[slot];
+        st.mapped = false;
+        if (copyEnqueued) {
+            if (!st.event) adlCheck(b200rs_event_create(m_handle, &st.event), "b200rs_event_create");
+            st.inFlight = st.event && b200rs_event_record(m_handle, st.event) == B200RS_OK;
+            if (!st.inFlight) waitForCompletion();
+        }
     }
 
     DeviceType m_type;
@@ -195,10 +232,10 @@ struct Device {
     unsigned int m_binaryFileVersion;
 
 private:
+    enum { NUM_STAGES = 2 };
+    struct Stage { void* p; size_t bytes; void* event; bool mapped; bool inFlight; };
     b200rs_device* m_handle;
-    mutable void* m_stage;
-    mutable size_t m_stageBytes;
-    mutable bool m_stageBusy;
+    mutable Stage m_stages[NUM_STAGES];
 };
 
 // Typed device allocation.  Public fields and their order follow the reference (Adl.h:201-220) so that
@@ -234,9 +271,17 @@ struct Buffer : public BufferBase {
     };
     bool m_allocated;
 
+    // Contents are defined on the device (something was written through adl / Pprims / uArray since the allocation).  A
+    // buffer that never was is mapped without the device -> host copy: the reference caller's first step is "map a fresh
+    // buffer, fill it on the host, unmap" (UnitTest/main.cpp:118-126).  Code that writes through the raw m_ptr calls this.
+    void markDeviceWritten() const { m_deviceWritten = true; }
+    bool isZeroCopy() const { return m_zeroCopy; }
+
 private:
     mutable u64 m_mappedElems;
-    mutable bool m_mapOwnsStage;
+    mutable int m_mapSlot;
+    mutable bool m_deviceWritten;
+    bool m_zeroCopy;
     inline void releaseStorage();
 };
 
@@ -347,14 +392,14 @@ void DeviceUtils::flush(const Device* device) {
 // ---- Buffer<T> -------------------------------------------------------------------------------------
 
 template <typename T>
-Buffer<T>::Buffer() : m_device(0), m_size(0), m_ptr(0), m_allocated(false), m_mappedElems(0), m_mapOwnsStage(false) {
+Buffer<T>::Buffer() : m_device(0), m_size(0), m_ptr(0), m_allocated(false), m_mappedElems(0), m_mapSlot(-1), m_deviceWritten(false), m_zeroCopy(false) {
     m_dx11.m_uav = 0;
     m_dx11.m_srv = 0;
 }
 
 template <typename T>
 Buffer<T>::Buffer(const Device* device, u64 nElems, BufferType type)
-    : m_device(0), m_size(0), m_ptr(0), m_allocated(false), m_mappedElems(0), m_mapOwnsStage(false) {
+    : m_device(0), m_size(0), m_ptr(0), m_allocated(false), m_mappedElems(0), m_mapSlot(-1), m_deviceWritten(false), m_zeroCopy(false) {
     m_dx11.m_uav = 0;
     m_dx11.m_srv = 0;
     allocate(device, nElems, type);
@@ -363,12 +408,19 @@ Buffer<T>::Buffer(const Device* device, u64 nElems, BufferType type)
 template <typename T>
 void Buffer<T>::releaseStorage() {
     if (m_allocated && m_ptr && m_device) {
-        adlCheck(b200rs_free(m_device->getHandle(), m_ptr), "b200rs_free");
+        if (m_zeroCopy) {
+            m_device->waitForCompletion();  // kernels may still be using the host block
+            adlCheck(b200rs_host_free(m_device->getHandle(), m_ptr), "b200rs_host_free");
+        } else {
+            adlCheck(b200rs_free(m_device->getHandle(), m_ptr), "b200rs_free");
+        }
         m_device->m_memoryUsage -= m_size * sizeof(T);
     }
     m_ptr = 0;
     m_size = 0;
     m_allocated = false;
+    m_zeroCopy = false;
+    m_deviceWritten = false;
 }
 
 template <typename T>
@@ -385,10 +437,11 @@ void Buffer<T>::setRawPtr(const Device* device, T* ptr, u64 size, BufferType typ
     m_device = device;
     m_ptr = ptr;
     m_size = size;
+    m_deviceWritten = true;  // foreign memory: assume it holds data
 }
 
 template <typename T>
-void Buffer<T>::allocate(const Device* device, u64 nElems, BufferType /*type*/) {
+void Buffer<T>::allocate(const Device* device, u64 nElems, BufferType type) {
     ADLASSERT(m_device == 0 || m_device == device);
     ADLASSERT(!m_allocated);
     m_device = device;
@@ -396,10 +449,16 @@ void Buffer<T>::allocate(const Device* device, u64 nElems, BufferType /*type*/) 
     m_ptr = 0;
     if (nElems == 0 || device == 0) return;
     void* p = 0;
-    if (!adlCheck(b200rs_malloc(device->getHandle(), nElems * sizeof(T), &p), "b200rs_malloc")) return;  // m_ptr = 0, m_size = 0 like AdlCL.inl:390-406
+    m_zeroCopy = type == BUFFER_ZERO_COPY;
+    if (m_zeroCopy) {  // pinned host memory, device-accessible under the same address
+        if (!adlCheck(b200rs_host_alloc(device->getHandle(), nElems * sizeof(T), &p), "b200rs_host_alloc")) { m_zeroCopy = false; return; }
+    } else if (!adlCheck(b200rs_malloc(device->getHandle(), nElems * sizeof(T), &p), "b200rs_malloc")) {
+        return;  // m_ptr = 0, m_size = 0 like AdlCL.inl:390-406
+    }
     m_ptr = (T*)p;
     m_size = nElems;
     m_allocated = true;
+    m_deviceWritten = false;
     device->m_memoryUsage += nElems * sizeof(T);
 }
 
@@ -407,6 +466,7 @@ template <typename T>
 void Buffer<T>::write(const T* hostSrcPtr, u64 nElems, u64 dstOffsetNElems, SyncObject*) {
     if (nElems == 0) return;
     ADLASSERT(nElems + dstOffsetNElems <= m_size);
+    m_deviceWritten = true;
     adlCheck(b200rs_memcpy_h2d(m_device->getHandle(), m_ptr + dstOffsetNElems, hostSrcPtr, nElems * sizeof(T)), "b200rs_memcpy_h2d");
 }
 
@@ -421,6 +481,7 @@ template <typename T>
 void Buffer<T>::write(const Buffer<T>& src, u64 nElems, SyncObject*) {
     if (nElems == 0) return;
     ADLASSERT(nElems <= m_size && nElems <= src.m_size);
+    m_deviceWritten = true;
     adlCheck(b200rs_memcpy_d2d(m_device->getHandle(), m_ptr, src.m_ptr, nElems * sizeof(T)), "b200rs_memcpy_d2d");
 }
 
@@ -429,20 +490,39 @@ void Buffer<T>::read(Buffer<T>& dst, u64 nElems, u64 offsetNElems, SyncObject*) 
     ADLASSERT(offsetNElems == 0);
     if (nElems == 0) return;
     ADLASSERT(nElems <= m_size && nElems <= dst.m_size);
+    dst.markDeviceWritten();
     adlCheck(b200rs_memcpy_d2d(m_device->getHandle(), dst.m_ptr, m_ptr, nElems * sizeof(T)), "b200rs_memcpy_d2d");
 }
 
 template <typename T>
 void Buffer<T>::clear() {
-    if (m_size) adlCheck(b200rs_memset(m_device->getHandle(), m_ptr, 0, m_size * sizeof(T)), "b200rs_memset");
+    if (m_size == 0) return;
+    m_deviceWritten = true;
+    adlCheck(b200rs_memset(m_device->getHandle(), m_ptr, 0, m_size * sizeof(T)), "b200rs_memset");
 }
 
 template <typename T>
 void Buffer<T>::fill(void* pattern, int patternSize) {
-    // repeats `pattern` over the whole buffer (reference: AdlCL.inl:523-542 / AdlHost.inl:132-145)
+    // repeats `pattern` over the whole buffer ON THE DEVICE (reference: clEnqueueFillBuffer, AdlCL.inl:523-542;
+    // AdlHost.inl:132-145): patterns of 1, 2, 4, 8 or 16 bytes are widened to 16 (or 4) bytes and written by the library's fill
+    // kernel; other pattern sizes are expanded on the host once and copied.
     const u64 bytes = m_size * sizeof(T);
     ADLASSERT(patternSize > 0 && bytes % (u64)patternSize == 0);
     if (bytes == 0) return;
+    m_deviceWritten = true;
+    const bool pow2 = patternSize <= 16 && (patternSize & (patternSize - 1)) == 0;
+    if (pow2 && ((uintptr_t)m_ptr % 16 == 0) && bytes % 16 == 0) {
+        uint32_t wide[4];
+        for (int off = 0; off < 16; off += patternSize) memcpy((char*)wide + off, pattern, (size_t)patternSize);
+        adlCheck(b200rs_fill_u128(m_device->getHandle(), m_ptr, wide, bytes / 16), "b200rs_fill_u128");
+        return;
+    }
+    if (pow2 && patternSize <= 4 && ((uintptr_t)m_ptr % 4 == 0) && bytes % 4 == 0) {
+        uint32_t word = 0;
+        for (int off = 0; off < 4; off += patternSize) memcpy((char*)&word + off, pattern, (size_t)patternSize);
+        adlCheck(b200rs_fill_u32(m_device->getHandle(), (uint32_t*)m_ptr, word, bytes / 4), "b200rs_fill_u32");
+        return;
+    }
     char* host = new char[bytes];
     for (u64 off = 0; off < bytes; off += (u64)patternSize) memcpy(host + off, pattern, (size_t)patternSize);
     adlCheck(b200rs_memcpy_h2d(m_device->getHandle(), m_ptr, host, bytes), "b200rs_memcpy_h2d");
@@ -456,13 +536,19 @@ T* Buffer<T>::getHostPtr(u64 size) const {
     const u64 n = (size == (u64)-1 || size > m_size) ? m_size : size;
     if (n == 0) return 0;
     Buffer<T>* self = const_cast<Buffer<T>*>(this);
-    bool owns = false;
-    void* stage = m_device->acquireStage(n * sizeof(T), &owns);
+    if (m_zeroCopy) {  // the buffer IS host memory: valid once the device work on it has completed (the caller waits, as for any map)
+        self->m_cl.m_hostPtr = (char*)m_ptr;
+        m_mappedElems = n;
+        return m_ptr;
+    }
+    int slot = -1;
+    void* stage = m_device->acquireStage(n * sizeof(T), &slot);
     if (!stage) return 0;
     self->m_cl.m_hostPtr = (char*)stage;
     m_mappedElems = n;
-    m_mapOwnsStage = owns;
-    adlCheck(b200rs_memcpy_d2h(m_device->getHandle(), stage, m_ptr, n * sizeof(T)), "b200rs_memcpy_d2h");  // async; caller waits
+    m_mapSlot = slot;
+    // a buffer nothing was ever written to holds no data worth the copy (the caller is about to fill the view)
+    if (m_deviceWritten) adlCheck(b200rs_memcpy_d2h(m_device->getHandle(), stage, m_ptr, n * sizeof(T)), "b200rs_memcpy_d2h");  // async; caller waits
     return (T*)stage;
 }
 
@@ -471,11 +557,19 @@ void Buffer<T>::returnHostPtr(T* ptr) const {
     if (ptr == 0) return;
     ADLASSERT((char*)ptr == m_cl.m_hostPtr);
     Buffer<T>* self = const_cast<Buffer<T>*>(this);
-    adlCheck(b200rs_memcpy_h2d(m_device->getHandle(), m_ptr, ptr, m_mappedElems * sizeof(T)), "b200rs_memcpy_h2d");
-    m_device->waitForCompletion();  // the staging block is recycled right away
-    m_device->releaseStage(ptr, m_mapOwnsStage);
     self->m_cl.m_hostPtr = 0;
+    if (m_zeroCopy) {
+        m_mappedElems = 0;
+        m_deviceWritten = true;
+        return;
+    }
+    // non-blocking: the copy out of the stage is stream-ordered in front of whatever uses the buffer next; the stage is
+    // recycled when the event recorded behind the copy has passed (Device::releaseStage)
+    const bool ok = adlCheck(b200rs_memcpy_h2d(m_device->getHandle(), m_ptr, ptr, m_mappedElems * sizeof(T)), "b200rs_memcpy_h2d");
+    m_deviceWritten = true;
+    m_device->releaseStage(ptr, m_mapSlot, ok);
     m_mappedElems = 0;
+    m_mapSlot = -1;
 }
 
 template <typename T>

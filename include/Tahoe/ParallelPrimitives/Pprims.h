@@ -40,6 +40,16 @@ public:
     // any n >= 0
     void radixSort(const adl::Device* device, const adl::Buffer<u32>& inout, int n, int sortBits = 32);
 
+    // New capability (the reference is single-device, Adl/CL/AdlCL.inl:284-303): this rank's part of the key-value sort of an
+    // input partitioned over `comm.world` GPUs, one Pprims per rank -- b200rs_dist_sort_pairs_u32 (include/b200rs.h): top-digit
+    // histogram, all-gather, on-device plan, fused partition + peer stores, barrier, local stable sort.  `recvBases[r]` is a
+    // device-visible address of rank r's receive buffer (own included; capacity `recvCapacity` pairs on every rank), the two
+    // collectives are the caller's (b200rs_dist_comm).  Returns the number of pairs now sorted at recvBases[comm.rank] (the
+    // ranks' results in rank order are the stable sort of the inputs in rank order), or -1 when a rank's share would exceed
+    // recvCapacity (nothing is exchanged).  Waits for the device once, to read that count.
+    long long radixSortDistributed(const adl::Device* device, const b200rs_dist_comm& comm, const u64* recvBases, u64 recvCapacity,
+                                   const adl::Buffer<uint2>& in, int n);
+
     // Element-wise primitives: dst[i] = src[i] / dst[i] = src for i < n.  The reference declares them on uArray
     // (Pprims.cpp:31-121; commented out there, the OpenCL kernels CopyIntKernel ... FillF4Kernel are still
     // shipped, PprimsKernels.cl:9-48); the Buffer overloads are what those forward to.  Asynchronous.

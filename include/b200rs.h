@@ -150,6 +150,31 @@ int b200rs_scatter_pairs_to_parts(b200rs_device* dev, const b200rs_pair* in, uin
                                   const uint8_t* digit_to_part, const uint64_t* part_base_addr, const uint64_t* n_dev /* optional: device-side
                                   element count <= n (0 = do nothing) */, void* temp, size_t* temp_bytes);
 /*
+ * The exchange step of the multi-GPU sort for FEW destinations (parts <= 32): the same stable partition as
+ * b200rs_scatter_pairs_to_parts -- digit -> part through digit_to_part[256], part p's pairs appended in input order at byte
+ * address part_base_addr[p] (any memory this device can store to: local, or a peer's, mapped through b200rs_ipc_import) -- by
+ * a kernel built for long runs: ranking in registers, one look-back word per (tile, part), one bulk copy (TMA) per part and
+ * tile.  n_dev (device pointer, may be NULL): the number of pairs is min(n, *n_dev).  Temp: size query as usual.
+ * New capability (the reference is single-device, Adl/CL/AdlCL.inl:284-303); SURVEY.md section 8e step 3.
+ */
+int b200rs_exchange_pairs(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, int bits, const uint8_t* digit_to_part,
+                          const uint64_t* part_base_addr, int parts, const uint64_t* n_dev, void* temp, size_t* temp_bytes);
+/*
+ * The same exchange with destinations that own arbitrary KEY RANGES: the part of a pair is the number of thresholds
+ * splitters[0 .. parts - 2] (device, ascending 64-bit values; 2^32 = "no key reaches it") its key is >= to.  Used by the
+ * splitter plan of oclradixsort_b200/dist.py, which finds exact quantile keys -- and splits a key that alone exceeds a
+ * rank's share by source rank, through per-source thresholds -- so that any distribution is balanced.
+ */
+int b200rs_exchange_pairs_by_splitters(b200rs_device* dev, const b200rs_pair* in, uint64_t n, const uint64_t* splitters,
+                                       const uint64_t* part_base_addr, int parts, void* temp, size_t* temp_bytes);
+/*
+ * hist_out[j][d] (device, count x 256 x u64) = pairs whose key bits above the digit at `shift` equal prefixes[j] (device,
+ * count <= 31 values) and whose digit (key >> shift) & 255 is d; shift in {0, 8, 16, 24} (24: the prefixes must be 0).  One
+ * refinement round of the splitter plan.
+ */
+int b200rs_filtered_histograms_pairs(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, const uint32_t* prefixes, int count,
+                                     uint64_t* hist_out);
+/*
  * Exchange plan computed on the device, so the multi-GPU sort needs no host round trip: from the all-gathered
  * top-digit histograms hist_all[world][256] it derives contiguous digit ranges per rank (about N/world pairs each),
  * lut_out[256] (digit -> destination rank), part_base_out[256] (where THIS rank's pairs for destination d start:
@@ -161,6 +186,39 @@ int b200rs_dist_plan(b200rs_device* dev, const uint64_t* hist_all, int world, in
 /* b200rs_sort_pairs_u32 whose element count min(n_max, *n_dev) is read on the device (temp is sized for n_max). */
 int b200rs_sort_pairs_u32_devn(b200rs_device* dev, b200rs_pair* inout, uint64_t n_max, const uint64_t* n_dev, int sort_bits,
                                void* temp, size_t* temp_bytes);
+/*
+ * The whole partitioned sort of one rank as ONE call (replaces nothing in the reference, which is
+ * single-device: Adl/CL/AdlCL.inl:284-303; this is what Tahoe::Pprims::radixSortDistributed calls).  One rank per GPU;
+ * rank r's `in` slices, in rank order, are the global input order.  The caller supplies the two collectives the path
+ * needs -- the library itself links no communication library:
+ *   allgather(user, send_dev, recv_dev, bytes)  every rank contributes `bytes` from send_dev; recv_dev receives world x bytes
+ *                                               in rank order.  Device pointers.  Must be ordered with the handle's stream
+ *                                               (enqueue on that stream, or synchronise it before and return when done).
+ *   barrier(user)                               returns (or is stream-ordered) after every rank's work enqueued so far on its
+ *                                               handle's stream has completed: peer stores have landed.
+ * Steps: top-digit histogram -> allgather -> on-device plan (contiguous digit ranges of about N / world pairs per rank) ->
+ * b200rs_exchange_pairs straight into the ranks' receive buffers recv_base[0 .. world) (device-visible addresses of EVERY
+ * rank's receive buffer, own included; peers' through b200rs_ipc_import or peer access) -> barrier -> local stable sort of
+ * what arrived.  The sorted pairs of this rank are left at recv_base[rank]; counts_dev[1] (device, 2 x u64) = how many;
+ * status_dev[0] = 1 when a rank's share exceeds recv_capacity_pairs (nothing is exchanged then; the caller re-plans, e.g.
+ * oclradixsort_b200/dist.py's splitter path).  No host round trip inside.  Equal keys keep global input order: the
+ * concatenation of the ranks' outputs is the stable sort of the concatenated input.  Temp: size query as usual
+ * (recv_capacity_pairs must be the same on every rank).
+ */
+typedef int (*b200rs_allgather_fn)(void* user, const void* send_dev, void* recv_dev, size_t bytes);
+typedef int (*b200rs_barrier_fn)(void* user);
+typedef struct b200rs_dist_comm {
+    int rank, world;
+    b200rs_allgather_fn allgather;
+    b200rs_barrier_fn barrier;
+    void* user;
+} b200rs_dist_comm;
+int b200rs_dist_sort_pairs_u32(b200rs_device* dev, const b200rs_dist_comm* comm, const uint64_t* recv_base /* host array [world] */,
+                               uint64_t recv_capacity_pairs, const b200rs_pair* in, uint64_t n, uint64_t* counts_dev, uint32_t* status_dev,
+                               void* temp, size_t* temp_bytes);
+/* One process driving several GPUs (e.g. one host thread per rank): lets `dev` load from / store to memory of CUDA device
+ * peer_device_idx directly (cudaDeviceEnablePeerAccess; already-enabled is not an error). */
+int b200rs_enable_peer_access(b200rs_device* dev, int peer_device_idx);
 /* CUDA IPC for one-process-per-GPU jobs: export a b200rs_malloc'ed buffer, map a peer's buffer, unmap it. */
 int b200rs_ipc_export(b200rs_device* dev, void* ptr, unsigned char handle_out[64]);
 int b200rs_ipc_import(b200rs_device* dev, const unsigned char handle[64], void** ptr);
@@ -210,6 +268,11 @@ int b200rs_event_record(b200rs_device* dev, void* event);       /* on the handle
 /* Waits for stop_event, then *ms_out = device time between the two events. */
 int b200rs_event_elapsed_ms(b200rs_device* dev, void* start_event, void* stop_event, float* ms_out);
 int b200rs_event_destroy(b200rs_device* dev, void* event);
+/* *done = 1 when everything enqueued before the event's last record has finished (never blocks); b200rs_event_synchronize
+ * blocks until then.  Used by adl::Buffer's non-blocking unmap (the pinned stage of returnHostPtr is recycled when its
+ * event has passed; reference: non-blocking clEnqueueUnmapMemObject, AdlCL.inl:557-565). */
+int b200rs_event_query(b200rs_device* dev, void* event, int* done);
+int b200rs_event_synchronize(b200rs_device* dev, void* event);
 
 #ifdef __cplusplus
 }

@@ -57,8 +57,13 @@ SIGNATURES = {
     "b200rs_digit_histogram_pairs": (_int, [c_dev, _vp, _u64, _int, _int, _vp]),
     "b200rs_partition_pairs": (_int, [c_dev, _vp, _vp, _u64, _int, _int, _vp, _vp, _vp, _P(_sz)]),
     "b200rs_scatter_pairs_to_parts": (_int, [c_dev, _vp, _u64, _int, _int, _vp, _vp, _vp, _vp, _P(_sz)]),
+    "b200rs_exchange_pairs": (_int, [c_dev, _vp, _u64, _int, _int, _vp, _vp, _int, _vp, _vp, _P(_sz)]),
+    "b200rs_dist_sort_pairs_u32": (_int, [c_dev, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _P(_sz)]),
+    "b200rs_exchange_pairs_by_splitters": (_int, [c_dev, _vp, _u64, _vp, _vp, _int, _vp, _P(_sz)]),
+    "b200rs_filtered_histograms_pairs": (_int, [c_dev, _vp, _u64, _int, _vp, _int, _vp]),
     "b200rs_dist_plan": (_int, [c_dev, _vp, _int, _int, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "b200rs_sort_pairs_u32_devn": (_int, [c_dev, _vp, _u64, _vp, _int, _vp, _P(_sz)]),
+    "b200rs_enable_peer_access": (_int, [c_dev, _int]),
     "b200rs_ipc_export": (_int, [c_dev, _vp, ctypes.c_char_p]),
     "b200rs_ipc_import": (_int, [c_dev, ctypes.c_char_p, _P(_vp)]),
     "b200rs_ipc_release": (_int, [c_dev, _vp]),
@@ -75,6 +80,8 @@ SIGNATURES = {
     "b200rs_event_record": (_int, [c_dev, _vp]),
     "b200rs_event_elapsed_ms": (_int, [c_dev, _vp, _vp, _P(ctypes.c_float)]),
     "b200rs_event_destroy": (_int, [c_dev, _vp]),
+    "b200rs_event_query": (_int, [c_dev, _vp, _P(_int)]),
+    "b200rs_event_synchronize": (_int, [c_dev, _vp]),
 }
 
 _lib = None

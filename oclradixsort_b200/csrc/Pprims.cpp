@@ -55,26 +55,32 @@ bool primArgsOk(const adl::Device* device, int n, u64 dstSize, u64 srcSize) {
 
 void Pprims::copy(const adl::Device* device, adl::Buffer<int>& dst, const adl::Buffer<int>& src, int n) {
     if (!primArgsOk(device, n, dst.getSize(), src.getSize())) return;
+    dst.markDeviceWritten();
     adl::adlCheck(b200rs_copy_u32(device->getHandle(), (uint32_t*)dst.m_ptr, (const uint32_t*)src.m_ptr, (uint64_t)n), "b200rs_copy_u32");
 }
 void Pprims::copy(const adl::Device* device, adl::Buffer<u32>& dst, const adl::Buffer<u32>& src, int n) {
     if (!primArgsOk(device, n, dst.getSize(), src.getSize())) return;
+    dst.markDeviceWritten();
     adl::adlCheck(b200rs_copy_u32(device->getHandle(), (uint32_t*)dst.m_ptr, (const uint32_t*)src.m_ptr, (uint64_t)n), "b200rs_copy_u32");
 }
 void Pprims::copy(const adl::Device* device, adl::Buffer<float4>& dst, const adl::Buffer<float4>& src, int n) {
     if (!primArgsOk(device, n, dst.getSize(), src.getSize())) return;
+    dst.markDeviceWritten();
     adl::adlCheck(b200rs_copy_u128(device->getHandle(), dst.m_ptr, src.m_ptr, (uint64_t)n), "b200rs_copy_u128");
 }
 void Pprims::fill(const adl::Device* device, adl::Buffer<int>& dst, int src, int n) {
     if (!primArgsOk(device, n, dst.getSize(), (u64)n)) return;
+    dst.markDeviceWritten();
     adl::adlCheck(b200rs_fill_u32(device->getHandle(), (uint32_t*)dst.m_ptr, (uint32_t)src, (uint64_t)n), "b200rs_fill_u32");
 }
 void Pprims::fill(const adl::Device* device, adl::Buffer<u32>& dst, u32 src, int n) {
     if (!primArgsOk(device, n, dst.getSize(), (u64)n)) return;
+    dst.markDeviceWritten();
     adl::adlCheck(b200rs_fill_u32(device->getHandle(), (uint32_t*)dst.m_ptr, src, (uint64_t)n), "b200rs_fill_u32");
 }
 void Pprims::fill(const adl::Device* device, adl::Buffer<float4>& dst, const float4& src, int n) {
     if (!primArgsOk(device, n, dst.getSize(), (u64)n)) return;
+    dst.markDeviceWritten();
     uint32_t words[4];
     memcpy(words, &src, sizeof(words));
     adl::adlCheck(b200rs_fill_u128(device->getHandle(), dst.m_ptr, words, (uint64_t)n), "b200rs_fill_u128");
@@ -103,6 +109,7 @@ void Pprims::scan(const adl::Device* device, adl::Buffer<int>& dst, const adl::B
         return;
     }
     ADLASSERT((u64)n <= dst.getSize() && (u64)n <= src.getSize());
+    dst.markDeviceWritten();
     size_t need = 0;
     if (!adl::adlCheck(b200rs_exclusive_scan_u32(device->getHandle(), 0, 0, (uint64_t)n, 0, 0, &need), "b200rs_exclusive_scan_u32(size)")) return;
     const size_t totalSlot = (need + 255) / 256 * 256;  // one extra word behind the scan's own scratch holds the total
@@ -133,6 +140,32 @@ void Pprims::radixSort(const adl::Device* device, const adl::Buffer<uint2>& inou
     if (!temp) return;
     size_t have = m_tempBytes;
     adl::adlCheck(b200rs_sort_pairs_u32(device->getHandle(), (b200rs_pair*)inout.m_ptr, (uint64_t)n, sortBits, temp, &have), "b200rs_sort_pairs_u32");
+}
+
+long long Pprims::radixSortDistributed(const adl::Device* device, const b200rs_dist_comm& comm, const u64* recvBases, u64 recvCapacity,
+                                       const adl::Buffer<uint2>& in, int n) {
+    if (!isGpuDevice(device) || n < 0 || !recvBases) {
+        ADLASSERT(0);
+        return -1;
+    }
+    ADLASSERT((u64)n <= in.getSize());
+    size_t need = 0;
+    if (!adl::adlCheck(b200rs_dist_sort_pairs_u32(device->getHandle(), &comm, 0, recvCapacity, 0, (uint64_t)n, 0, 0, 0, &need), "b200rs_dist_sort_pairs_u32(size)"))
+        return -1;
+    char* temp = (char*)reserveTemp(device, (need + 255) / 256 * 256 + 256);  // + [counts 2 x u64 | status u32]
+    if (!temp) return -1;
+    uint64_t* counts = (uint64_t*)(temp + (need + 255) / 256 * 256);
+    uint32_t* status = (uint32_t*)(counts + 2);
+    size_t have = need;
+    uint64_t recv[32];
+    for (int r = 0; r < comm.world && r < 32; ++r) recv[r] = recvBases[r];
+    if (!adl::adlCheck(b200rs_dist_sort_pairs_u32(device->getHandle(), &comm, recv, recvCapacity, (const b200rs_pair*)in.m_ptr, (uint64_t)n, counts, status,
+                                                  temp, &have), "b200rs_dist_sort_pairs_u32"))
+        return -1;
+    uint64_t host[3] = {0, 0, 0};
+    adl::adlCheck(b200rs_memcpy_d2h(device->getHandle(), host, counts, sizeof(host)), "b200rs_memcpy_d2h");
+    device->waitForCompletion();
+    return (uint32_t)host[2] != 0 ? -1 : (long long)host[1];
 }
 
 void Pprims::radixSort(const adl::Device* device, const adl::Buffer<u32>& inout, int n, int sortBits) {

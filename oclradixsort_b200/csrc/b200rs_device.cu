@@ -262,6 +262,27 @@ int b200rs_event_elapsed_ms(b200rs_device* dev, void* start_event, void* stop_ev
     return B200RS_OK;
 }
 
+int b200rs_event_query(b200rs_device* dev, void* event, int* done) {
+    if (!dev || !event || !done) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    const cudaError_t e = cudaEventQuery((cudaEvent_t)event);
+    if (e == cudaErrorNotReady) {
+        (void)cudaGetLastError();
+        *done = 0;
+        return B200RS_OK;
+    }
+    B200RS_CUDA(e);
+    *done = 1;
+    return B200RS_OK;
+}
+
+int b200rs_event_synchronize(b200rs_device* dev, void* event) {
+    if (!dev || !event) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    B200RS_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+    return B200RS_OK;
+}
+
 int b200rs_event_destroy(b200rs_device* dev, void* event) {
     if (!dev) return B200RS_ERR_INVALID_ARGUMENT;
     if (!event) return B200RS_OK;

@@ -523,7 +523,6 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
     const uint32_t wend = lead + size;
     const int mine_n = wend > (uint32_t)tid ? (int)((wend - (uint32_t)tid + THREADS - 1) / THREADS) : 0;
     const bool skip0 = (uint32_t)tid < lead;
-    const int cta_n = (int)((wend + THREADS - 1) / THREADS);  // items any thread of the CTA holds (uniform): the rest is skipped outright
     auto is_valid = [&](int i) { return i < mine_n && !(i == 0 && skip0); };
     uint32_t key[IPT];
 #pragma unroll
@@ -544,13 +543,12 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) {
             const int i = i0 + j;
-            old[j] = 0;
-            if (i < IPT && i < cta_n) old[j] = atom_add_shared_if(is_valid(i), cnt_base + msd_word_offset<CHUNKS>(key[i]), 1u << ((key[i] & 7u) << 2));  // 0 where not valid
+            if (i < IPT) old[j] = atom_add_shared_if(is_valid(i), cnt_base + msd_word_offset<CHUNKS>(key[i]), 1u << ((key[i] & 7u) << 2));  // 0 where not valid
         }
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) {
             const int i = i0 + j;
-            if (i < IPT && i < cta_n) {
+            if (i < IPT) {
                 const uint32_t r = (old[j] >> ((key[i] & 7u) << 2)) & 15u;  // (not valid: 0)
                 worst = max(worst, r);
                 ranks[i >> 3] |= r << (4 * (i & 7));
@@ -625,7 +623,6 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
     const unsigned char* wp_bytes = reinterpret_cast<const unsigned char*>(s.wp);
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-        if (i >= cta_n) break;  // uniform
         const bool valid = is_valid(i);  // (a key outside the bucket reads the words of key 0 and stores to a dummy slot)
         const uint32_t sh = (key[i] & 7u) << 2;
         const uint32_t word = *reinterpret_cast<const uint32_t*>(cnt_bytes + msd_word_offset<CHUNKS>(key[i]));

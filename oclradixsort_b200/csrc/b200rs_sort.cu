@@ -1294,6 +1294,190 @@ extern "C" int b200rs_scatter_pairs_to_parts(b200rs_device* dev, const b200rs_pa
 
 namespace {
 
+// ---- exchange kernel of the multi-GPU sort: stable partition into FEW parts + bulk stores into peer memory ------------
+// Replaces the 256-digit scatter pass with a part table (onesweep_kernel<..., LUT, ABS>) for the exchange step: with at most
+// 32 destinations a tile's run per destination is kilobytes long, so
+//   * ranking needs no shared-memory atomics: the lanes holding the same part find each other with five ballots, and
+//     lane p of every warp keeps the warp's running count of part p in a REGISTER (its own match mask comes from the same
+//     five ballots); a lane fetches its group's base with one shuffle;
+//   * the look-back table has one word per (tile, part) instead of 256 per tile;
+//   * every run is staged at the same 16-byte phase as its destination and leaves the SM as ONE cp.async.bulk (TMA,
+//     shared -> global) per part -- the destination may be another GPU's memory (CUDA IPC mapping, NVLink): the copy engine
+//     streams it while the CTA's threads are already gone -- plus at most one 8-byte element at each ragged end.
+// Same stability argument as the scatter passes: warp-striped load order, per-warp counts, ticket-ordered tiles.
+constexpr int XP_THREADS = 256, XP_IPT = 16, XP_WARPS = XP_THREADS / 32, XP_TILE = XP_THREADS * XP_IPT, XP_MAX_PARTS = 32;
+struct XpSmem {
+    alignas(128) uint2 staged[XP_TILE + 2 * XP_MAX_PARTS];  // every run may start one element late and end one early
+    uint32_t warp_base[XP_WARPS][XP_MAX_PARTS];             // warp counts, then the warp's first slot inside the part's run
+    uint32_t region[XP_MAX_PARTS];                          // staged slot of the part's first element
+    uint32_t count[XP_MAX_PARTS];
+    unsigned long long dst[XP_MAX_PARTS];                   // byte address of the part's run in its destination
+    uint8_t lut[RADIX];
+    unsigned long long splitter[XP_MAX_PARTS];
+    uint32_t tile;
+    unsigned long long n_eff;
+};
+
+// SPLIT: the part of a pair is the number of thresholds (parts - 1 ascending 64-bit values, `splitters`) its key reaches,
+// instead of a table lookup on one digit: destinations then own arbitrary key ranges (exact quantiles, dist.py's splitter plan).
+template <bool BULK, bool SPLIT>
+__global__ void __launch_bounds__(XP_THREADS, 4)
+exchange_partition_kernel(const uint2* __restrict__ in, uint64_t n, int shift, uint32_t digit_mask, const uint8_t* __restrict__ digit_lut,
+                          const unsigned long long* __restrict__ splitters,
+                          const unsigned long long* __restrict__ part_base /*[parts] byte addresses, 8-byte aligned*/, int parts,
+                          uint64_t* lookback /*[tiles][XP_MAX_PARTS] tagged words, zeroed*/, uint32_t* ticket,
+                          const unsigned long long* __restrict__ n_dev, uint32_t minus_one) {
+    extern __shared__ __align__(128) unsigned char xp_smem_raw[];
+    XpSmem& s = *reinterpret_cast<XpSmem*>(xp_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s.tile = atomicAdd(ticket, 1u);
+        s.n_eff = n_dev ? min((unsigned long long)n, *n_dev) : (unsigned long long)n;
+    }
+    if (!SPLIT && tid < RADIX) s.lut[tid] = digit_lut[tid];
+    if (SPLIT && tid < XP_MAX_PARTS) s.splitter[tid] = tid < parts - 1 ? splitters[tid] : ~0ull;
+    __syncthreads();
+    n = s.n_eff;
+    const uint32_t tile = s.tile;
+    const uint64_t tile_base = (uint64_t)tile * XP_TILE;
+    if (tile_base >= n) return;  // surplus CTAs of a grid sized for the upper bound
+    const uint32_t valid = (uint32_t)min((uint64_t)XP_TILE, n - tile_base);
+    const uint32_t slice = warp * (32 * XP_IPT) + lane;
+
+    uint2 elem[XP_IPT];
+    const uint2* __restrict__ src = in + tile_base + slice;
+#pragma unroll
+    for (int i = 0; i < XP_IPT; ++i)
+        if (slice + i * 32 < valid) elem[i] = __ldg(src + i * 32);
+
+    // ---- ranking in registers ----
+    const uint32_t lt = lanemask_lt();
+    uint32_t xk[5];  // lane p's selector: all-ones where bit k of p is CLEAR (its match mask takes the complement of that ballot)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) xk[k] = ((lane >> k) & 1) ? 0u : 0xffffffffu;
+    uint32_t cnt = 0;                  // lane p: pairs of part p seen so far by this warp
+    uint32_t rec[XP_IPT / 2];          // per item: part | rank << 5, two per register
+#pragma unroll
+    for (int i = 0; i < XP_IPT / 2; ++i) rec[i] = 0;
+#pragma unroll
+    for (int i = 0; i < XP_IPT; ++i) {
+        const bool live = slice + i * 32 < valid;
+        uint32_t part = 0;
+        if (SPLIT) {
+            if (live)
+                for (int j = 0; j < parts - 1; ++j) part += (unsigned long long)elem[i].x >= s.splitter[j] ? 1u : 0u;
+        } else {
+            part = live ? (uint32_t)s.lut[(elem[i].x >> shift) & digit_mask] : 0u;
+        }
+        const uint32_t live_lanes = __ballot_sync(0xffffffffu, live);
+        uint32_t peers = live_lanes, owner = live_lanes;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const uint32_t b = __ballot_sync(0xffffffffu, (part >> k) & 1u);
+            peers &= ((part >> k) & 1u) ? b : ~b;   // lanes whose bit k equals mine
+            owner &= b ^ xk[k];                      // lanes whose bit k equals bit k of MY LANE NUMBER
+        }
+        const uint32_t base = __shfl_sync(0xffffffffu, cnt, (int)part);  // count of my part before this item
+        cnt += (uint32_t)__popc(owner);
+        const uint32_t r = base + (uint32_t)__popc(peers & lt);
+        rec[i >> 1] |= (part | (r << 5)) << (16 * (i & 1));
+    }
+    s.warp_base[warp][lane] = cnt;
+    __syncthreads();
+
+    // ---- warp 0, lane p = part p: totals, look-back, layout of the staged tile ----
+    if (warp == 0) {
+        uint32_t total = 0;
+        if (lane < parts) {
+#pragma unroll
+            for (int w = 0; w < XP_WARPS; ++w) {
+                const uint32_t c = s.warp_base[w][lane];
+                s.warp_base[w][lane] = total;
+                total += c;
+            }
+        }
+        uint64_t exclusive = 0;
+        if (lane < parts) {
+            const uint64_t TAG_PARTIAL = 1ull << LB_TAG_SHIFT, TAG_INCLUSIVE = 2ull << LB_TAG_SHIFT;
+            uint64_t* mine = lookback + (uint64_t)tile * XP_MAX_PARTS + lane;
+            if (tile != 0) {
+                st_relaxed_u64(mine, TAG_PARTIAL | total);
+                const uint64_t* p = mine - XP_MAX_PARTS;  // tile 0 always publishes INCLUSIVE: the walk ends there
+                int32_t ahead = (int32_t)tile;
+                bool done = false;
+                while (!done) {
+                    uint64_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) w[j] = j < ahead ? ld_relaxed_u64(p - j * XP_MAX_PARTS) : 0ull;
+                    int consumed = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t tag = (uint32_t)(w[j] >> LB_TAG_SHIFT);
+                        if (!done && consumed == j && tag != 0) {
+                            exclusive += w[j] & LB_VALUE_MASK;
+                            consumed = j + 1;
+                            done = tag == 2;
+                        }
+                    }
+                    p -= consumed * XP_MAX_PARTS;
+                    ahead -= consumed;
+                }
+            }
+            st_relaxed_u64(mine, TAG_INCLUSIVE | (exclusive + total));
+        }
+        const unsigned long long dst = lane < parts ? part_base[lane] + 8ull * exclusive : 0ull;
+        const uint32_t phase = (uint32_t)(dst >> 3) & 1u;            // the run starts in the upper half of a 16-byte chunk
+        const uint32_t padded = (phase + total + 1u) & ~1u;           // slots the run occupies, a whole number of chunks
+        uint32_t inc = padded;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += y;
+        }
+        s.region[lane] = inc - padded + phase;
+        s.count[lane] = total;
+        s.dst[lane] = dst;
+    }
+    __syncthreads();
+
+    // ---- every pair to its staged slot ----
+    const uint32_t staged = smem_addr(&s.staged[0]);
+#pragma unroll
+    for (int i = 0; i < XP_IPT; ++i) {
+        if (slice + i * 32 < valid) {
+            const uint32_t pr = (rec[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+            const uint32_t part = pr & 31u, r = pr >> 5;
+            st_shared(staged + 8u * (s.region[part] + s.warp_base[warp][part] + r), elem[i]);
+        }
+    }
+    if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the staged tile is read by the async proxy below
+    __syncthreads();
+
+    // ---- write-out ----
+    if (BULK) {
+        if (warp == 0 && lane < parts) {
+            uint32_t a = s.region[lane], c = s.count[lane];
+            unsigned long long g = s.dst[lane];
+            if (c && (a & 1u)) {  // ragged head: one element up to the 16-byte boundary
+                *reinterpret_cast<uint2*>(g) = s.staged[a];
+                ++a; --c; g += 8;
+            }
+            const uint32_t body = c & ~1u;
+            if (body) bulk_copy_s2g(reinterpret_cast<void*>(g), staged + 8u * a, body * 8u);
+            if (c & 1u) *reinterpret_cast<uint2*>(g + 8ull * body) = s.staged[a + body];
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the copy's reads
+        }
+    } else {
+        for (int p = 0; p < parts; ++p) {
+            const uint32_t a = s.region[p], c = s.count[p];
+            uint2* g = reinterpret_cast<uint2*>(s.dst[p]);
+            for (uint32_t j = tid; j < c; j += XP_THREADS) g[j] = s.staged[a + j];
+        }
+    }
+    (void)minus_one;
+}
+
 // ---- on-device exchange plan (one CTA of 256 threads): keeps the multi-GPU sort free of host round trips ----
 // hist_all[s][b] = pairs on source rank s with top digit b.  Digit ranges are contiguous per destination; the edge
 // between rank r-1 and r is the digit boundary whose cumulative count is closest to r*N/P (exact integer compare,
@@ -1373,6 +1557,95 @@ dist_plan_kernel(const unsigned long long* __restrict__ hist_all, int P, int me,
 
 }  // namespace
 
+namespace {
+int exchange_impl(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, int bits, const uint8_t* digit_to_part, const uint64_t* splitters,
+                  const uint64_t* part_base_addr, int parts, const uint64_t* n_dev, void* temp, size_t* temp_bytes) {
+    if (!dev || !temp_bytes || parts < 1 || parts > XP_MAX_PARTS) return B200RS_ERR_INVALID_ARGUMENT;
+    const uint64_t tiles = (n + XP_TILE - 1) / XP_TILE;
+    if (tiles > 0x7fffffffull) return B200RS_ERR_TOO_LARGE;
+    const size_t need = 256 + b200rs_align_up((size_t)tiles * XP_MAX_PARTS * sizeof(uint64_t), 256);
+    if (!temp) {
+        *temp_bytes = need;
+        return B200RS_OK;
+    }
+    if (*temp_bytes < need) return B200RS_ERR_TEMP_TOO_SMALL;
+    if (n == 0) return B200RS_OK;
+    if (!in || (!digit_to_part && !splitters) || !part_base_addr || ((uintptr_t)temp & 255u) || ((uintptr_t)in & 7u)) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    B200RS_CUDA(cudaMemsetAsync(temp, 0, need, dev->stream));
+    const bool bulk = !b200rs_exp_env("B200RS_XP_NO_BULK", 0);
+    auto kernel = splitters ? (bulk ? exchange_partition_kernel<true, true> : exchange_partition_kernel<false, true>)
+                            : (bulk ? exchange_partition_kernel<true, false> : exchange_partition_kernel<false, false>);
+    const size_t smem = sizeof(XpSmem);
+    B200RS_TRY(b200rs_kernel_setup(dev, (const void*)kernel, smem));
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(temp);
+    uint64_t* lookback = reinterpret_cast<uint64_t*>(static_cast<char*>(temp) + 256);
+    {
+        b200rs_launch_scope scope(dev, splitters ? "exchange_pairs_splitters" : "exchange_pairs", n, 2ull * n * sizeof(uint2));
+        kernel<<<(unsigned)tiles, XP_THREADS, smem, dev->stream>>>(reinterpret_cast<const uint2*>(in), n, shift, (1u << bits) - 1u, digit_to_part,
+                                                                  reinterpret_cast<const unsigned long long*>(splitters),
+                                                                  reinterpret_cast<const unsigned long long*>(part_base_addr), parts, lookback, ticket,
+                                                                  reinterpret_cast<const unsigned long long*>(n_dev), 0xffffffffu);
+    }
+    B200RS_CUDA(cudaGetLastError());
+    return B200RS_OK;
+}
+
+// Histograms of one key digit restricted to keys with given higher bits: hist_out[j][d] = pairs whose bits above the digit
+// equal prefixes[j] and whose digit is d (the splitter plan refines its boundaries with these, one digit per round).
+constexpr int FH_MAX = 31;
+__global__ void __launch_bounds__(HIST_THREADS)
+filtered_histogram_kernel(const uint2* __restrict__ in, uint64_t n, int shift, const uint32_t* __restrict__ prefixes, int count,
+                          unsigned long long* __restrict__ out /*[count][RADIX]*/) {
+    extern __shared__ uint32_t fh_hist[];  // [count][RADIX]
+    __shared__ uint32_t s_prefix[FH_MAX];
+    for (int i = threadIdx.x; i < count * RADIX; i += HIST_THREADS) fh_hist[i] = 0;
+    if (threadIdx.x < count) s_prefix[threadIdx.x] = prefixes[threadIdx.x];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * HIST_THREADS;
+    for (uint64_t i = (uint64_t)blockIdx.x * HIST_THREADS + threadIdx.x; i < n; i += stride) {
+        const uint32_t key = in[i].x;
+        const uint32_t high = shift + RADIX_BITS >= 32 ? 0u : key >> (shift + RADIX_BITS), d = (key >> shift) & (RADIX - 1);
+        for (int j = 0; j < count; ++j)
+            if (high == s_prefix[j]) atomicAdd(&fh_hist[j * RADIX + d], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < count * RADIX; i += HIST_THREADS)
+        if (fh_hist[i]) atomicAdd(&out[i], (unsigned long long)fh_hist[i]);
+}
+}  // namespace
+
+extern "C" int b200rs_exchange_pairs(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, int bits, const uint8_t* digit_to_part,
+                                     const uint64_t* part_base_addr, int parts, const uint64_t* n_dev, void* temp, size_t* temp_bytes) {
+    if (shift < 0 || bits < 1 || bits > RADIX_BITS || shift + bits > 32) return B200RS_ERR_INVALID_ARGUMENT;
+    return exchange_impl(dev, in, n, shift, bits, digit_to_part, nullptr, part_base_addr, parts, n_dev, temp, temp_bytes);
+}
+
+extern "C" int b200rs_exchange_pairs_by_splitters(b200rs_device* dev, const b200rs_pair* in, uint64_t n, const uint64_t* splitters,
+                                                  const uint64_t* part_base_addr, int parts, void* temp, size_t* temp_bytes) {
+    if (temp && !splitters && parts > 1) return B200RS_ERR_INVALID_ARGUMENT;
+    static const uint64_t none = 0;
+    (void)none;
+    return exchange_impl(dev, in, n, 0, 8, nullptr, splitters ? splitters : part_base_addr /* parts == 1: never read */, part_base_addr, parts, nullptr, temp, temp_bytes);
+}
+
+extern "C" int b200rs_filtered_histograms_pairs(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, const uint32_t* prefixes, int count,
+                                                uint64_t* hist_out) {
+    if (!dev || !hist_out || !prefixes || (n && !in) || shift < 0 || shift > 24 || (shift & 7) || count < 1 || count > FH_MAX) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    B200RS_CUDA(cudaMemsetAsync(hist_out, 0, sizeof(uint64_t) * RADIX * count, dev->stream));
+    if (n == 0) return B200RS_OK;
+    uint64_t blocks = (n + (uint64_t)HIST_THREADS * 8 - 1) / ((uint64_t)HIST_THREADS * 8);
+    if (blocks > (uint64_t)dev->num_sms * 4) blocks = (uint64_t)dev->num_sms * 4;
+    {
+        b200rs_launch_scope scope(dev, "filtered_histograms_pairs", n, n * sizeof(uint2));
+        filtered_histogram_kernel<<<(unsigned)blocks, HIST_THREADS, (size_t)count * RADIX * sizeof(uint32_t), dev->stream>>>(
+            reinterpret_cast<const uint2*>(in), n, shift, prefixes, count, reinterpret_cast<unsigned long long*>(hist_out));
+    }
+    B200RS_CUDA(cudaGetLastError());
+    return B200RS_OK;
+}
+
 extern "C" int b200rs_dist_plan(b200rs_device* dev, const uint64_t* hist_all, int world, int rank, const uint64_t* peer_base, uint64_t capacity,
                                 uint64_t n_in, uint8_t* lut_out, uint64_t* part_base_out, uint64_t* counts_out, uint32_t* status_out) {
     if (!dev || !hist_all || !peer_base || !lut_out || !part_base_out || !counts_out || !status_out || world < 1 || world > 32 || rank < 0 || rank >= world)
@@ -1395,11 +1668,61 @@ extern "C" int b200rs_sort_pairs_u32_devn(b200rs_device* dev, b200rs_pair* inout
                             reinterpret_cast<const unsigned long long*>(n_dev));
 }
 
-namespace {
+// ---- the whole partitioned sort of one rank (see include/b200rs.h) -------------------------------------------------------
+extern "C" int b200rs_dist_sort_pairs_u32(b200rs_device* dev, const b200rs_dist_comm* comm, const uint64_t* recv_base, uint64_t recv_capacity_pairs,
+                                          const b200rs_pair* in, uint64_t n, uint64_t* counts_dev, uint32_t* status_dev, void* temp, size_t* temp_bytes) {
+    if (!dev || !comm || !temp_bytes || comm->world < 1 || comm->world > XP_MAX_PARTS || comm->rank < 0 || comm->rank >= comm->world) return B200RS_ERR_INVALID_ARGUMENT;
+    const int world = comm->world;
+    // temp: [own histogram 256 x u64][gathered world x 256 x u64][peer bases 256 x u64][part bases 256 x u64][lut 256][exchange temp][local sort temp]
+    size_t xp_bytes = 0, sort_bytes = 0;
+    B200RS_TRY(b200rs_exchange_pairs(dev, nullptr, n, 24, 8, nullptr, nullptr, world, nullptr, nullptr, &xp_bytes));
+    B200RS_TRY(b200rs_sort_pairs_u32_devn(dev, nullptr, recv_capacity_pairs, nullptr, 32, nullptr, &sort_bytes));
+    const size_t hist_off = 0, gathered_off = hist_off + RADIX * 8, peers_off = gathered_off + (size_t)world * RADIX * 8, parts_off = peers_off + RADIX * 8,
+                 lut_off = parts_off + RADIX * 8, xp_off = lut_off + 256, sort_off = xp_off + b200rs_align_up(xp_bytes, 256),
+                 need = sort_off + b200rs_align_up(sort_bytes, 256);
+    if (!temp) {
+        *temp_bytes = need;
+        return B200RS_OK;
+    }
+    if (*temp_bytes < need) return B200RS_ERR_TEMP_TOO_SMALL;
+    if (!recv_base || !counts_dev || !status_dev || (n && !in) || !comm->allgather || !comm->barrier || ((uintptr_t)temp & 255u)) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    char* base = static_cast<char*>(temp);
+    uint64_t* hist = reinterpret_cast<uint64_t*>(base + hist_off);
+    uint64_t* gathered = reinterpret_cast<uint64_t*>(base + gathered_off);
+    uint64_t* peers = reinterpret_cast<uint64_t*>(base + peers_off);
+    uint64_t* part_base = reinterpret_cast<uint64_t*>(base + parts_off);
+    uint8_t* lut = reinterpret_cast<uint8_t*>(base + lut_off);
+    B200RS_CUDA(cudaMemcpyAsync(peers, recv_base, (size_t)world * 8, cudaMemcpyHostToDevice, dev->stream));  // (pageable source: staged by the runtime before the call returns)
+    B200RS_TRY(b200rs_digit_histogram_pairs(dev, in, n, 24, 8, hist));
+    // the all-gather also orders this step after every rank's previous local sort: nobody overwrites a receive buffer that is still being read
+    {
+        const int rc = comm->allgather(comm->user, hist, gathered, RADIX * 8);
+        if (rc != 0) return rc;
+    }
+    B200RS_TRY(b200rs_dist_plan(dev, gathered, world, comm->rank, peers, recv_capacity_pairs, n, lut, part_base, counts_dev, status_dev));
+    size_t have = xp_bytes;
+    B200RS_TRY(b200rs_exchange_pairs(dev, in, n, 24, 8, lut, part_base, world, counts_dev, base + xp_off, &have));
+    {
+        const int rc = comm->barrier(comm->user);  // every rank's stores have landed before anyone sorts
+        if (rc != 0) return rc;
+    }
+    have = sort_bytes;
+    return b200rs_sort_pairs_u32_devn(dev, reinterpret_cast<b200rs_pair*>(recv_base[comm->rank]), recv_capacity_pairs, counts_dev + 1, 32, base + sort_off, &have);
+}
 
-// ---- CUDA IPC: lets one-process-per-GPU ranks store into each other's buffers over NVLink ----
-}  // namespace
-
+extern "C" int b200rs_enable_peer_access(b200rs_device* dev, int peer_device_idx) {
+    if (!dev || peer_device_idx < 0) return B200RS_ERR_INVALID_ARGUMENT;
+    if (peer_device_idx == dev->device_idx) return B200RS_OK;
+    b200rs_device_guard guard(dev);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device_idx, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        (void)cudaGetLastError();
+        return B200RS_OK;
+    }
+    B200RS_CUDA(e);
+    return B200RS_OK;
+}
 extern "C" int b200rs_ipc_export(b200rs_device* dev, void* ptr, unsigned char handle_out[64]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     if (!dev || !ptr || !handle_out) return B200RS_ERR_INVALID_ARGUMENT;

@@ -6,10 +6,20 @@ are the global input order.  For inputs beyond one GPU's HBM:
 
   1. local histogram of the TOP key digit (8 bits)                        b200rs_digit_histogram_pairs
   2. all-gather of the per-rank histograms (256 x P counts)               dist.all_gather_into_tensor  (NCCL)
-     -> every rank derives the same plan: contiguous digit ranges -> ranks with about N/P pairs each
-  3. local STABLE partition by destination rank                           b200rs_partition_pairs
-  4. exchange, receive slots ordered by source rank                       dist.all_to_all_single over NVLink (NCCL)
-  5. local stable LSD sort of what was received                           b200rs_sort_pairs_u32
+     -> every rank derives the same plan ON THE DEVICE: contiguous digit ranges -> ranks with about N/P pairs each
+  3. ONE kernel: local STABLE partition by destination rank, every run stored straight into the destination GPU's
+     receive buffer over NVLink (peer memory mapped through CUDA IPC, bulk copies)   b200rs_exchange_pairs
+  4. barrier (an all-reduce of one word): every rank's stores have landed
+  5. local stable LSD sort of what was received                           b200rs_sort_pairs_u32_devn
+Steps 1-5 are ONE C call, b200rs_dist_sort_pairs_u32, which takes the two collectives as callbacks (the library links no
+communication library); this module supplies torch.distributed for them.  exchange="nccl" keeps the baseline: partition
+into a local send buffer + dist.all_to_all_single.
+
+Skew.  Digit ranges cannot split a hot top digit; when the plan of step 2 would overflow a receive buffer the sort is
+re-planned with EXACT QUANTILE SPLITTERS (SplitterPlan): three more rounds of 256-bin histograms restricted to the bins
+the boundaries fall in narrow every boundary down to one 32-bit key, and a key that is itself too frequent is split by
+source rank (all copies of a key on lower ranks go first: stability is kept), so any distribution -- all keys equal
+included -- is balanced to within one source's count of one key.
 
 Bit-exactness: 3 and 5 are stable and 4 keeps (source rank, position) order = global input order inside every
 destination, and destinations own disjoint, increasing key ranges, so the concatenation of the ranks' outputs is
@@ -72,6 +82,76 @@ def plan_exchange(hist: np.ndarray) -> dict:
             "recv_offset": recv_offset, "bin_offset": bin_offset}
 
 
+class SplitterPlan:
+    """Exact quantile splitters from per-source digit histograms, refined one digit per round (pure numpy; every rank
+    computes the same plan from the same all-gathered histograms).
+
+      plan = SplitterPlan(H0)                H0[s, b]: pairs on source s with top digit b
+      for level in 1, 2, 3:
+          plan.refine(H)                     H[s, j, d]: pairs on source s whose key bits above digit (3 - level) equal
+                                             plan.prefixes()[j] and whose digit (3 - level) is d
+      res = plan.finish()
+
+    Boundary j (between destination j and j + 1) aims at t_j = j * N // P pairs below it.  After the last round it is an
+    exact key K_j with, per source, the number of pairs below K_j and equal to K_j; the pairs equal to K_j go below the
+    boundary for the first tie_j sources only -- source order is input order, so this keeps the sort stable."""
+
+    def __init__(self, hist0):
+        h = np.asarray(hist0, dtype=np.int64)
+        self.P = h.shape[0]
+        assert h.shape == (self.P, NUM_BINS)
+        self.n_src = h.sum(axis=1)
+        self.N = int(self.n_src.sum())
+        self.J = self.P - 1
+        self.targets = np.array([(j * self.N) // self.P for j in range(1, self.P)], dtype=np.int64)
+        self.below = np.zeros((self.J, self.P), dtype=np.int64)   # pairs on source s below boundary j's current prefix
+        self.prefix = np.zeros(self.J, dtype=np.int64)
+        self.eq = np.zeros((self.J, self.P), dtype=np.int64)
+        self.level = 0
+        self._step(np.broadcast_to(h[:, None, :], (self.P, self.J, NUM_BINS)))
+
+    def _step(self, H):
+        """H[s, j, d] for the digit below the current prefixes."""
+        tot = H.sum(axis=0)  # [J, 256]
+        for j in range(self.J):
+            r = int(self.targets[j] - self.below[j].sum())
+            cum = np.concatenate([[0], np.cumsum(tot[j])])
+            d = int(np.searchsorted(cum, r, side="right")) - 1
+            d = min(max(d, 0), NUM_BINS - 1)
+            self.below[j] += H[:, j, :d].sum(axis=1)
+            self.prefix[j] = self.prefix[j] * NUM_BINS + d
+            self.eq[j] = H[:, j, d]
+
+    def prefixes(self):
+        return self.prefix.astype(np.uint32)
+
+    def refine(self, H):
+        H = np.asarray(H, dtype=np.int64).reshape(self.P, self.J, NUM_BINS)
+        self.level += 1
+        self._step(H)
+
+    def finish(self):
+        assert self.level == 3 or self.J == 0
+        P, J = self.P, self.J
+        L = np.zeros((P + 1, P), dtype=np.int64)  # L[j, s]: pairs of source s that go below boundary j
+        thr = np.zeros((P, max(J, 1)), dtype=np.uint64)
+        ties = []
+        for j in range(J):
+            r = int(self.targets[j] - self.below[j].sum())
+            ceq = np.concatenate([[0], np.cumsum(self.eq[j])])
+            tie = int(np.argmin(np.abs(ceq - r)))  # whole sources whose copies of K_j go below: the count closest to the target
+            ties.append(tie)
+            L[j + 1] = self.below[j] + np.where(np.arange(P) < tie, self.eq[j], 0)
+            thr[:, j] = np.uint64(self.prefix[j]) + (np.arange(P) < tie).astype(np.uint64)
+        L[P] = self.n_src
+        for j in range(1, P + 1):  # boundaries that coincide (a key hot enough to span several ranks) stay ordered
+            L[j] = np.maximum(L[j], L[j - 1])
+        send_counts = (L[1:] - L[:-1]).T.copy()  # [s, d]
+        recv_offset = np.cumsum(send_counts, axis=0) - send_counts
+        return {"thresholds": thr[:, :J], "keys": self.prefix.copy(), "ties": ties, "send_counts": send_counts, "recv_offset": recv_offset,
+                "recv_total": send_counts.sum(axis=0), "total": self.N}
+
+
 class CudaLocalOps:
     """The device side of the protocol on one B200, through the C ABI.  Buffers are torch int64 tensors (one
     element = one {key, value} pair, key in the low half -- the AoS layout of Tahoe::uint2)."""
@@ -81,6 +161,11 @@ class CudaLocalOps:
         self.torch = torch
         self.device, self.pprims = device, pprims
         self.cuda = torch.device("cuda", device.device_idx)
+        # the library's kernels run on the handle's stream, torch's collectives and copies on torch's current stream: they
+        # must be the same stream, or nothing orders a histogram before its all-gather, a peer scatter before the barrier ...
+        if device.stream() != torch.cuda.current_stream(self.cuda).cuda_stream:
+            raise ValueError("DistributedPairSorter: create the Device on torch's current stream "
+                             "(DeviceUtils.allocate(..., cuda_stream=torch.cuda.current_stream().cuda_stream)) and keep that stream current")
         self._hist = torch.zeros(NUM_BINS, dtype=torch.int64, device=self.cuda)
         self._lut = torch.zeros(NUM_BINS, dtype=torch.uint8, device=self.cuda)
         self._counts = torch.zeros(NUM_BINS, dtype=torch.int64, device=self.cuda)
@@ -190,6 +275,79 @@ class CudaLocalOps:
     def to_host_matrix(self, t):
         return t.cpu().numpy()
 
+    # ---- the whole fast path as one C call (b200rs_dist_sort_pairs_u32) with torch.distributed behind its callbacks ----
+    def dist_sort_async(self, src, n, dist, world, rank, peers, capacity, flag):
+        t = self.torch
+        if not hasattr(self, "_cnts"):
+            self._cnts = t.zeros(2, dtype=t.int64, device=self.cuda)    # [0] pairs to scatter, [1] pairs received
+            self._status = t.zeros(1, dtype=t.int32, device=self.cuda)  # 1 = capacity exceeded, nothing exchanged
+        if not hasattr(self, "_comm"):
+            cuda = self.cuda
+
+            def allgather(user, send, recv, nbytes):
+                try:
+                    dist.all_gather_into_tensor(_tensor_from_ptr(t, recv, world * nbytes // 8, cuda), _tensor_from_ptr(t, send, nbytes // 8, cuda))
+                    return 0
+                except Exception:  # noqa: BLE001 -- must not unwind through the C frame
+                    return -1
+
+            def barrier(user):
+                try:
+                    dist.all_reduce(flag)  # stream-ordered: every rank's stores have landed before anyone's next kernel
+                    return 0
+                except Exception:  # noqa: BLE001
+                    return -1
+
+            AG = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+            BR = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p)
+
+            class Comm(ctypes.Structure):
+                _fields_ = [("rank", ctypes.c_int), ("world", ctypes.c_int), ("allgather", AG), ("barrier", BR), ("user", ctypes.c_void_p)]
+
+            self._callbacks = (AG(allgather), BR(barrier))  # kept alive as long as the ops object
+            self._comm = Comm(rank, world, self._callbacks[0], self._callbacks[1], None)
+            self._recv_base = (ctypes.c_uint64 * world)(*[int(a) for a in peers])
+        fn = lib().b200rs_dist_sort_pairs_u32
+        need = ctypes.c_size_t(0)
+        check(fn(self.device.handle, ctypes.byref(self._comm), self._recv_base, capacity, None, n, None, None, None, ctypes.byref(need)),
+              "b200rs_dist_sort_pairs_u32 (size)")
+        temp = self.pprims._scratch(self.device, need.value)
+        have = ctypes.c_size_t(temp.getSize())
+        check(fn(self.device.handle, ctypes.byref(self._comm), self._recv_base, capacity, ctypes.c_void_p(src.data_ptr()), n,
+                 ctypes.c_void_p(self._cnts.data_ptr()), ctypes.c_void_p(self._status.data_ptr()), ctypes.c_void_p(temp.m_ptr), ctypes.byref(have)),
+              "b200rs_dist_sort_pairs_u32")
+
+    # ---- splitter plan (skewed inputs) ----
+    def filtered_histograms(self, pairs, n, shift, prefixes: np.ndarray):
+        t = self.torch
+        J = len(prefixes)
+        pre = t.from_numpy(np.ascontiguousarray(prefixes, dtype=np.uint32).view(np.int32)).to(self.cuda)
+        out = t.zeros(J * NUM_BINS, dtype=t.int64, device=self.cuda)
+        check(lib().b200rs_filtered_histograms_pairs(self.device.handle, ctypes.c_void_p(pairs.data_ptr()), n, shift, ctypes.c_void_p(pre.data_ptr()), J,
+                                                     ctypes.c_void_p(out.data_ptr())), "b200rs_filtered_histograms_pairs")
+        return out
+
+    def exchange_by_splitters(self, src, n, thresholds: np.ndarray, part_base_addr: np.ndarray):
+        """Stable partition by key thresholds straight into the parts' base addresses (local or peer memory)."""
+        t = self.torch
+        parts = len(part_base_addr)
+        thr = t.from_numpy(np.ascontiguousarray(np.concatenate([thresholds, [0]]), dtype=np.uint64).view(np.int64)).to(self.cuda)
+        base = t.from_numpy(np.ascontiguousarray(part_base_addr, dtype=np.uint64).view(np.int64)).to(self.cuda)
+        fn = lib().b200rs_exchange_pairs_by_splitters
+        need = ctypes.c_size_t(0)
+        check(fn(self.device.handle, None, n, None, None, parts, None, ctypes.byref(need)), "b200rs_exchange_pairs_by_splitters (size)")
+        if self._temp is None or self._temp.numel() < need.value + 256:
+            self._temp = t.empty(need.value + 256, dtype=t.uint8, device=self.cuda)
+        tp = (self._temp.data_ptr() + 255) // 256 * 256
+        have = ctypes.c_size_t(need.value)
+        check(fn(self.device.handle, ctypes.c_void_p(src.data_ptr()), n, ctypes.c_void_p(thr.data_ptr()), ctypes.c_void_p(base.data_ptr()), parts,
+                 ctypes.c_void_p(tp), ctypes.byref(have)), "b200rs_exchange_pairs_by_splitters")
+        self._keep = (thr, base)  # alive until the kernel has run (the next call replaces them after a stream-ordered collective)
+
+    def partition_by_splitters(self, src, dst, n, thresholds: np.ndarray, part_counts: np.ndarray):
+        starts = np.cumsum(part_counts) - part_counts
+        self.exchange_by_splitters(src, n, thresholds, np.uint64(dst.data_ptr()) + 8 * starts.astype(np.uint64))
+
     def release(self):
         self._temp = None
 
@@ -209,7 +367,12 @@ class DistributedPairSorter:
         self.dist = dist
         self.ops = ops if ops is not None else CudaLocalOps(device, pprims)
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.capacity = int(capacity_pairs * slack) + 1024  # receive capacity; a plan that exceeds it raises
+        # receive capacity; a plan that exceeds it raises.  Every rank must use the SAME value (the on-device plan and the
+        # overflow decision compare every destination's share with it): the minimum over the ranks' requests.
+        caps = [None] * self.world
+        dist.all_gather_object(caps, int(capacity_pairs * slack) + 1024)
+        self.capacity = min(caps)
+        self.send_capacity = int(capacity_pairs)
         self.exchange = exchange or ("p2p" if getattr(self.ops, "supports_p2p", False) else "nccl")
         self.layout = layout
         self.last_plan = None
@@ -237,33 +400,64 @@ class DistributedPairSorter:
         return pairs
 
     def sort_async(self, pairs, n: int):
-        """p2p/dest only: enqueue the whole partitioned sort without any host round trip (histogram -> all-gather ->
-        on-device plan -> fused scatter into peer memory -> all-reduce barrier -> local sort with a device-side count).
-        Returns the receive buffer; call finish() for the element count (it synchronises and raises on overflow)."""
+        """p2p/dest only: enqueue the whole partitioned sort without any host round trip -- one call of
+        b200rs_dist_sort_pairs_u32 (histogram -> all-gather -> on-device plan -> fused partition + peer stores -> barrier ->
+        local sort with a device-side count).  Returns the receive buffer; call finish() for the element count (it
+        synchronises; a plan that overflowed a receive buffer exchanged nothing and reports status 1)."""
         assert self.exchange == "p2p" and self.layout == "dest"
-        ops, dist = self.ops, self.dist
         src = self._as_tensor(pairs, n)
-        hist = ops.histogram(src, n)
-        if not hasattr(self, "_gathered"):
-            self._gathered = hist.new_empty(self.world * NUM_BINS)
-        dist.all_gather_into_tensor(self._gathered, hist)  # also orders this step after every rank's previous local sort
-        ops.plan_async(self._gathered, self.world, self.rank, self._peers_dev, self.capacity, n)
-        ops.scatter_async(src, n)
-        dist.all_reduce(self._flag)  # every rank's stores have landed before anyone sorts
-        ops.local_sort_devn(self.recv, self.capacity)
+        self.ops.dist_sort_async(src, n, self.dist, self.world, self.rank, self.peers, self.capacity, self._flag)
         return self.recv
 
     def finish(self) -> int:
         m, status = self.ops.read_counts()
         if status != 0:
-            raise B200RSError(ERR_CAPACITY, f"distributed sort: a rank's share exceeds the receive capacity of {self.capacity} pairs")
+            raise B200RSError(ERR_CAPACITY, f"distributed sort: a rank's share exceeds the receive capacity of {self.capacity} pairs "
+                                            "(digit-range plan; DistributedPairSorter.sort re-plans with exact splitters)")
         return m
 
+    def _gather_matrix(self, t, cols):
+        g = t.new_empty(self.world * t.numel())
+        self.dist.all_gather_into_tensor(g, t)
+        return self.ops.to_host_matrix(g).reshape(self.world, *cols)
+
+    def sort_with_splitters(self, pairs, n: int):
+        """The skew-proof path: exact quantile splitters (SplitterPlan) from four rounds of 256-bin histograms, ties split by
+        source rank; then the same fused exchange (thresholds instead of a digit table) and the local sort."""
+        ops, dist = self.ops, self.dist
+        src = self._as_tensor(pairs, n)
+        plan = SplitterPlan(self._gather_matrix(ops.histogram(src, n), (NUM_BINS,)))  # (also orders this step after the previous local sorts)
+        if self.world > 1:
+            for level in (1, 2, 3):
+                h = ops.filtered_histograms(src, n, TOP_SHIFT - 8 * level, plan.prefixes())
+                plan.refine(self._gather_matrix(h, (self.world - 1, NUM_BINS)))
+        res = plan.finish()
+        self.last_plan = res
+        m = int(res["recv_total"][self.rank])
+        if int(res["recv_total"].max()) > self.capacity:  # same decision on every rank: nobody enters the exchange
+            raise B200RSError(ERR_CAPACITY, f"distributed sort: rank {int(res['recv_total'].argmax())} would receive {int(res['recv_total'].max())} pairs "
+                                            f"even with exact splitters (one key on one source exceeds the slack), capacity {self.capacity}")
+        if self.exchange == "p2p":
+            base = np.asarray(self.peers, dtype=np.uint64) + 8 * res["recv_offset"][self.rank].astype(np.uint64)
+            ops.exchange_by_splitters(src, n, res["thresholds"][self.rank], base)
+            dist.all_reduce(self._flag)  # every rank's stores have landed before anyone sorts
+        else:
+            assert n <= self.send_capacity
+            send_counts = res["send_counts"][self.rank]
+            ops.partition_by_splitters(src, self.send, n, res["thresholds"][self.rank], send_counts)
+            recv_counts = res["send_counts"][:, self.rank]
+            dist.all_to_all_single(self.recv[:m], self.send[:n], [int(c) for c in recv_counts], [int(c) for c in send_counts])
+        if m:
+            ops.local_sort(self.recv, m)
+        return self.recv[:m], m
+
     def sort(self, pairs, n: int):
-        if self.exchange == "p2p" and self.layout == "dest" and hasattr(self.ops, "plan_async"):
+        if self.exchange == "p2p" and self.layout == "dest" and hasattr(self.ops, "dist_sort_async"):
             out = self.sort_async(pairs, n)
-            m = self.finish()
-            return out[:m], m
+            m, status = self.ops.read_counts()
+            if status == 0:
+                return out[:m], m
+            return self.sort_with_splitters(pairs, n)  # the digit-range plan overflowed (skew): nothing was exchanged
         ops, dist = self.ops, self.dist
         src = self._as_tensor(pairs, n)
         hist = ops.histogram(src, n)
@@ -273,6 +467,8 @@ class DistributedPairSorter:
         self.last_plan = plan
         m = int(plan["recv_total"][self.rank])
         if int(plan["recv_total"].max()) > self.capacity:  # same decision on every rank: nobody enters the collective
+            if hasattr(ops, "filtered_histograms"):
+                return self.sort_with_splitters(pairs, n)
             raise B200RSError(ERR_CAPACITY, f"distributed sort: rank {int(plan['recv_total'].argmax())} would receive "
                                             f"{int(plan['recv_total'].max())} pairs, capacity {self.capacity}")
         if self.exchange == "p2p":
@@ -289,6 +485,7 @@ class DistributedPairSorter:
             ops.scatter(src, n, lut, base)
             dist.all_reduce(self._flag)  # every rank's stores have landed (kernel completion + collective) before anyone sorts
         else:
+            assert n <= self.send_capacity, "the send buffer holds capacity_pairs pairs"
             send_counts = plan["send_counts"][self.rank]
             ops.partition(src, self.send, n, plan["bin_to_rank"], send_counts)
             recv_counts = plan["send_counts"][:, self.rank]

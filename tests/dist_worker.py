@@ -22,6 +22,12 @@ def make_input(kind, rank, n):
         keys = (keys & np.uint32(0x0F00000F)) * np.uint32(0x11)
     elif kind == "skewtop":
         keys = keys >> np.uint32(2 * rank)
+    elif kind == "allequal":
+        keys[:] = 0xDEADBEEF
+    elif kind == "hotdigit":     # one top digit holds everything: digit ranges cannot balance it
+        keys = (keys & np.uint32(0x00FFFFFF)) | np.uint32(0x5A000000)
+    elif kind == "and3":
+        keys = keys & rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32) & rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
     kv = np.empty((n, 2), dtype=np.uint32)
     kv[:, 0], kv[:, 1] = keys, np.arange(n, dtype=np.uint32) + np.uint32(rank << 26)
     return kv
@@ -36,10 +42,13 @@ def main():
     ok = True
     modes = [("nccl", "dest"), ("p2p", "dest"), ("p2p", "bins")]
     cases = [("uniform", (1 << 20) + 17 * rank), ("lowentropy", 300_000), ("skewtop", 500_001)]
-    for (kind, n), (exchange, layout) in [(c, m) for c in cases for m in modes]:
+    # skewed inputs with the DEFAULT slack: the digit-range plan overflows and the sort re-plans with exact splitters
+    skewed = [("allequal", 400_000), ("hotdigit", 300_001), ("and3", (1 << 19) + 5)]
+    runs = [(c, m, float(world) + 0.5) for c in cases for m in modes] + [(c, m, 1.25) for c in skewed for m in modes[:2]]
+    for (kind, n), (exchange, layout), slack in runs:
         kv = make_input(kind, rank, n)
         src = torch.from_numpy(kv.view(np.int64).reshape(-1).copy()).cuda()
-        sorter = DistributedPairSorter(dev, pp, n + 64, dist, slack=float(world) + 0.5, exchange=exchange, layout=layout)
+        sorter = DistributedPairSorter(dev, pp, n + 64, dist, slack=slack, exchange=exchange, layout=layout)
         out, m = sorter.sort(src, n)
         out2, m2 = sorter.sort(src, n)  # a second call reuses the receive buffers
         assert m2 == m
@@ -52,7 +61,7 @@ def main():
             from oracle import pyoracle as po
             whole = np.concatenate([make_input(kind, r, sizes[r][0]) for r in range(world)])
             same = np.array_equal(np.concatenate(outs), po.sort_pairs(whole))
-            print(f"dist {kind} {exchange}/{layout}: per-rank in/out {sizes} bit-exact={same}", flush=True)
+            print(f"dist {kind} {exchange}/{layout} slack {slack}: per-rank in/out {sizes} bit-exact={same}", flush=True)
             ok = ok and same
         sorter.release()
     pp.release()

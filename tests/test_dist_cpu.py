@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from oclradixsort_b200.dist import NUM_BINS, DistributedPairSorter, plan_exchange
+from oclradixsort_b200.dist import NUM_BINS, DistributedPairSorter, SplitterPlan, plan_exchange
 from oracle import pyoracle as po
 
 
@@ -64,6 +64,22 @@ class NumpyOps:
         a = pairs[:m].numpy().view(np.uint32).reshape(m, 2)
         a[:] = po.sort_pairs(np.ascontiguousarray(a))
 
+    def filtered_histograms(self, pairs, n, shift, prefixes):
+        keys = pairs[:n].numpy().view(np.uint32)[0::2]
+        high = (keys.astype(np.uint64) >> np.uint64(shift + 8)).astype(np.uint32)
+        digit = (keys >> np.uint32(shift)) & np.uint32(255)
+        out = np.stack([np.bincount(digit[high == p], minlength=NUM_BINS) for p in prefixes]) if len(prefixes) else np.zeros((0, NUM_BINS))
+        return torch.from_numpy(out.astype(np.int64).reshape(-1))
+
+    def partition_by_splitters(self, src, dst, n, thresholds, part_counts):
+        a = src[:n].numpy()
+        keys = a.view(np.uint32)[0::2].astype(np.uint64)
+        part = np.zeros(n, dtype=np.int64)
+        for t in thresholds:
+            part += keys >= np.uint64(t)
+        assert np.array_equal(np.bincount(part, minlength=len(part_counts)), part_counts)
+        dst[:n] = torch.from_numpy(a[np.argsort(part, kind="stable")])
+
     def to_host_matrix(self, t):
         return t.numpy()
 
@@ -74,6 +90,12 @@ class NumpyOps:
 def _make_input(kind, rank, n):
     rng = np.random.default_rng(100 + rank)
     keys = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    if kind == "allequal":
+        keys[:] = 0xDEADBEEF
+    elif kind == "hotkey":
+        keys[: (3 * n) // 4] = 0x12345678
+    elif kind == "hotdigit":
+        keys = (keys & np.uint32(0x00FFFFFF)) | np.uint32(0x77000000)
     if kind == "lowentropy":
         keys = (keys & np.uint32(0x03000003)) | np.uint32(0x40000000)
     elif kind == "ragged":
@@ -88,7 +110,8 @@ def _worker(rank, world, port, kind, ns, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     n = ns[rank]
     kv = _make_input(kind, rank, n)
-    sorter = DistributedPairSorter(None, None, max(ns), dist, ops=NumpyOps(), slack=8.0, exchange="nccl")
+    slack = 1.25 if kind in ("allequal", "hotkey", "hotdigit") else 8.0  # skewed inputs: the default slack, so the digit-range plan overflows
+    sorter = DistributedPairSorter(None, None, max(ns), dist, ops=NumpyOps(), slack=slack, exchange="nccl")
     out, m = sorter.sort(torch.from_numpy(kv.view(np.int64).reshape(-1).copy()), n)
     np.save(os.path.join(out_dir, f"out{rank}.npy"), out.numpy().view(np.uint32).reshape(m, 2))
     dist.barrier()
@@ -101,10 +124,74 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("kind,ns", [("uniform", (5000, 5000)), ("lowentropy", (4096, 3000)), ("ragged", (7001, 1))])
+@pytest.mark.parametrize("kind,ns", [("uniform", (5000, 5000)), ("lowentropy", (4096, 3000)), ("ragged", (7001, 1)),
+                                     ("allequal", (6000, 6000)), ("hotkey", (5000, 5000)), ("hotdigit", (5000, 4000))])
 def test_protocol_world2_gloo_matches_single_stable_sort(tmp_path, kind, ns):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), kind, ns, str(tmp_path)), nprocs=world, join=True)
     got = np.concatenate([np.load(tmp_path / f"out{r}.npy") for r in range(world)])
     whole = np.concatenate([_make_input(kind, r, ns[r]) for r in range(world)])
     assert np.array_equal(got, po.sort_pairs(whole))  # rank-order concatenation == one stable sort of the whole input
+
+
+def _brute_force_split(keys_per_src):
+    """Runs SplitterPlan the way DistributedPairSorter.sort_with_splitters does, with numpy histograms."""
+    P = len(keys_per_src)
+    plan = SplitterPlan(np.stack([np.bincount(k >> np.uint32(24), minlength=NUM_BINS) for k in keys_per_src]))
+    for level in (1, 2, 3):
+        if P == 1:
+            break
+        shift = 24 - 8 * level
+        pref = plan.prefixes()
+        H = np.zeros((P, P - 1, NUM_BINS), dtype=np.int64)
+        for s, k in enumerate(keys_per_src):
+            high = (k.astype(np.uint64) >> np.uint64(shift + 8)).astype(np.uint32)
+            d = (k >> np.uint32(shift)) & np.uint32(255)
+            for j in range(P - 1):
+                H[s, j] = np.bincount(d[high == pref[j]], minlength=NUM_BINS)
+        plan.refine(H)
+    return plan.finish()
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 8])
+@pytest.mark.parametrize("kind", ["uniform", "allequal", "two", "ragged", "and3", "hotkey"])
+def test_splitter_plan_is_exact_stable_and_balanced(P, kind):
+    rng = np.random.default_rng(P * 31 + len(kind))
+    keys = []
+    for s in range(P):
+        n = 2000
+        u = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        if kind == "allequal":
+            u[:] = 0xDEADBEEF
+        elif kind == "two":
+            u = np.where(u & 1, np.uint32(5), np.uint32(0xFFFFFFFF))
+        elif kind == "ragged":
+            u = u >> np.uint32(2 * s)
+        elif kind == "and3":
+            u = u & rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32) & rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        elif kind == "hotkey":
+            u[: n * 3 // 4] = 0x12345678
+        keys.append(u)
+    res = _brute_force_split(keys)
+    got = [[] for _ in range(P)]
+    for s, k in enumerate(keys):
+        part = np.zeros(k.size, dtype=np.int64)
+        for j in range(P - 1):
+            part += k.astype(np.uint64) >= res["thresholds"][s, j]
+        assert np.array_equal(np.bincount(part, minlength=P), res["send_counts"][s])
+        for d in range(P):
+            sel = np.nonzero(part == d)[0]
+            got[d].append(np.stack([k[sel].astype(np.int64), np.full(sel.size, s), sel], axis=1))
+    allk = np.concatenate(keys).astype(np.int64)
+    src = np.concatenate([np.full(k.size, s) for s, k in enumerate(keys)])
+    pos = np.concatenate([np.arange(k.size) for k in keys])
+    order = np.lexsort((pos, src, allk))
+    want = np.stack([allk[order], src[order], pos[order]], axis=1)
+    parts = []
+    for d in range(P):
+        a = np.concatenate(got[d])
+        parts.append(a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))])  # a stable local sort keeps (source, position) order
+    assert np.array_equal(np.concatenate(parts), want)  # rank-order concatenation == the stable sort of the whole input
+    # equal shards: balanced to within ONE source's count of the key a boundary falls on (exact when no key is hot)
+    spread = int(res["recv_total"].max() - res["recv_total"].min())
+    assert spread <= (2000 if kind in ("two", "hotkey") else 1), (spread, res["recv_total"])

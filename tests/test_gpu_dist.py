@@ -96,4 +96,113 @@ def test_partitioned_sort_two_gpus_nccl():
            "--master-port", "29533", os.path.join(ROOT, "tests", "dist_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
-    assert r.stdout.count("bit-exact=True") == 9, r.stdout[-2000:]  # 3 inputs x {nccl, p2p/dest, p2p/bins}
+    assert r.stdout.count("bit-exact=True") == 15, r.stdout[-3000:]  # 3 inputs x {nccl, p2p/dest, p2p/bins} + 3 skewed inputs x {nccl, p2p/dest}
+
+
+def test_cpp_caller_of_the_partitioned_sort(tmp_path):
+    """tests/cpp/dist_dropin.cpp: Tahoe::Pprims::radixSortDistributed (b200rs_dist_sort_pairs_u32) driven from C++, one host
+    thread per GPU, collectives = pthread barrier + peer copies; checked against std::stable_sort of the whole input."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    exe = os.path.join(ROOT, "tools", "_build", "dist_dropin")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", ROOT, "dist_test"], check=True)
+    for world, n in ((2, 300007), (min(torch.cuda.device_count(), 4), 1 << 20)):
+        r = subprocess.run([exe, str(world), str(n)], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "DIST DROPIN OK" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
+def _device_ops():
+    import torch
+
+    import oclradixsort_b200 as ob
+    from oclradixsort_b200.dist import CudaLocalOps
+    d = ob.DeviceUtils.allocate(ob.TYPE_CL, 0, cuda_stream=torch.cuda.current_stream().cuda_stream)
+    p = ob.Pprims()
+    return ob, d, p, CudaLocalOps(d, p)
+
+
+def test_exchange_kernel_matches_numpy_stable_partition():
+    """b200rs_exchange_pairs (the few-parts kernel with bulk copies) on one GPU: the parts' base addresses point into one
+    local buffer, so the result must equal numpy's stable partition; sizes around the 4096-pair tile, 1..32 parts, runs
+    that start on odd element boundaries (ragged 16-byte ends), empty parts."""
+    import torch
+
+    from oclradixsort_b200._lib import check, lib
+    ob, d, p, ops = _device_ops()
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 4095, 4096, 4097, 123457, 1_000_003):
+        for parts in (1, 2, 3, 8, 32):
+            kv = np.empty((n, 2), dtype=np.uint32)
+            kv[:, 0] = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+            kv[:, 1] = np.arange(n, dtype=np.uint32)
+            top = kv[:, 0] >> 24
+            edges = np.sort(rng.integers(0, 257, size=parts - 1))
+            lut = np.searchsorted(edges, np.arange(256), side="right").astype(np.uint8)
+            counts = np.bincount(lut[top], minlength=parts)
+            gap = 3  # every part starts 3 pairs after the previous one ends: odd and even destination phases
+            starts = np.cumsum(counts + gap) - (counts + gap)
+            src = torch.from_numpy(kv.view(np.int64).reshape(-1).copy()).cuda()
+            dst = torch.full((n + gap * parts + 8,), -1, dtype=torch.int64, device="cuda")
+            lut_d = torch.from_numpy(lut).cuda()
+            base_d = torch.from_numpy((np.uint64(dst.data_ptr()) + 8 * starts.astype(np.uint64)).view(np.int64)).cuda()
+            need = ctypes.c_size_t(0)
+            fn = lib().b200rs_exchange_pairs
+            check(fn(d.handle, None, n, 24, 8, None, None, parts, None, None, ctypes.byref(need)), "size")
+            temp = torch.empty(need.value + 256, dtype=torch.uint8, device="cuda")
+            tp = (temp.data_ptr() + 255) // 256 * 256
+            check(fn(d.handle, ctypes.c_void_p(src.data_ptr()), n, 24, 8, ctypes.c_void_p(lut_d.data_ptr()), ctypes.c_void_p(base_d.data_ptr()), parts, None,
+                     ctypes.c_void_p(tp), ctypes.byref(need)), "b200rs_exchange_pairs")
+            torch.cuda.synchronize()
+            got = dst.cpu().numpy()
+            order = np.argsort(lut[top], kind="stable")
+            want = np.full(got.shape, -1, dtype=np.int64)
+            sorted_pairs = kv[order].view(np.int64).reshape(-1)
+            at = 0
+            for q in range(parts):
+                want[starts[q]:starts[q] + counts[q]] = sorted_pairs[at:at + counts[q]]
+                at += counts[q]
+            assert np.array_equal(got, want), (n, parts)  # (also: nothing written outside the runs)
+    ops.release(); p.release(); ob.DeviceUtils.deallocate(d)
+
+
+def test_filtered_histograms_and_splitter_exchange_match_numpy():
+    import torch
+    ob, d, p, ops = _device_ops()
+    rng = np.random.default_rng(6)
+    for n in (1, 5000, 777_777):
+        kv = np.empty((n, 2), dtype=np.uint32)
+        kv[:, 0] = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32) & rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+        kv[:, 1] = np.arange(n, dtype=np.uint32)
+        keys = kv[:, 0]
+        src = torch.from_numpy(kv.view(np.int64).reshape(-1).copy()).cuda()
+        for shift in (16, 8, 0):
+            prefixes = np.unique(keys >> np.uint32(shift + 8))[:5].astype(np.uint32) if shift + 8 < 32 else np.zeros(1, dtype=np.uint32)
+            prefixes = np.concatenate([prefixes, [np.uint32(0x00ABCDEF >> shift)]]).astype(np.uint32)
+            h = ops.filtered_histograms(src, n, shift, prefixes).cpu().numpy().reshape(len(prefixes), 256)
+            high = (keys.astype(np.uint64) >> np.uint64(shift + 8)).astype(np.uint32)
+            digit = (keys >> np.uint32(shift)) & np.uint32(255)
+            for j, pre in enumerate(prefixes):
+                assert np.array_equal(h[j], np.bincount(digit[high == pre], minlength=256)), (n, shift, j)
+        for parts in (1, 2, 5, 8):
+            thr = np.sort(rng.integers(0, 2**32 + 1, size=parts - 1, dtype=np.uint64))
+            if parts > 2:
+                thr[1] = thr[0]  # two boundaries on the same key: an empty part
+            part = np.zeros(n, dtype=np.int64)
+            for t in thr:
+                part += keys.astype(np.uint64) >= t
+            counts = np.bincount(part, minlength=parts)
+            starts = np.cumsum(counts + 1) - (counts + 1)
+            dst = torch.full((n + parts + 8,), -1, dtype=torch.int64, device="cuda")
+            ops.exchange_by_splitters(src, n, thr, np.uint64(dst.data_ptr()) + 8 * starts.astype(np.uint64))
+            torch.cuda.synchronize()
+            got = dst.cpu().numpy()
+            sorted_pairs = kv[np.argsort(part, kind="stable")].view(np.int64).reshape(-1)
+            want = np.full(got.shape, -1, dtype=np.int64)
+            at = 0
+            for q in range(parts):
+                want[starts[q]:starts[q] + counts[q]] = sorted_pairs[at:at + counts[q]]
+                at += counts[q]
+            assert np.array_equal(got, want), (n, parts)
+    ops.release(); p.release(); ob.DeviceUtils.deallocate(d)
