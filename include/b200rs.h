@@ -183,7 +183,9 @@ int b200rs_filtered_histograms_pairs(b200rs_device* dev, const b200rs_pair* in, 
  */
 int b200rs_dist_plan(b200rs_device* dev, const uint64_t* hist_all, int world, int rank, const uint64_t* peer_base, uint64_t capacity,
                      uint64_t n_in, uint8_t* lut_out, uint64_t* part_base_out, uint64_t* counts_out, uint32_t* status_out);
-/* b200rs_sort_pairs_u32 whose element count min(n_max, *n_dev) is read on the device (temp is sized for n_max). */
+/* b200rs_sort_pairs_u32 whose element count min(n_max, *n_dev) is read on the device (temp is sized for n_max).  Only the
+ * first *n_dev elements are sorted; with an ODD number of passes (sort_bits <= 8 or in 17..24) the final copy back covers
+ * n_max elements, so inout[*n_dev .. n_max) then holds unspecified values. */
 int b200rs_sort_pairs_u32_devn(b200rs_device* dev, b200rs_pair* inout, uint64_t n_max, const uint64_t* n_dev, int sort_bits,
                                void* temp, size_t* temp_bytes);
 /*

@@ -33,6 +33,44 @@ class Device:
         self.m_type = TYPE_CL
         self.m_memoryUsage = 0  # bytes held by Buffers (Adl.h:150; checked in DeviceUtils.deallocate)
         self.device_idx = device_idx
+        # pinned staging ring of Buffer.getHostPtr / returnHostPtr, as in include/Adl/Adl.h (Device::acquireStage)
+        self._stages = [{"ptr": 0, "bytes": 0, "event": None, "mapped": False, "in_flight": False} for _ in range(2)]
+
+    def _acquire_stage(self, nbytes: int):
+        """(slot, pinned address): a block no live mapping holds and no copy still reads."""
+        for wait in (False, True):
+            for i, st in enumerate(self._stages):
+                if st["mapped"]:
+                    continue
+                if st["in_flight"]:
+                    if wait:
+                        check(lib().b200rs_event_synchronize(self.handle, st["event"]), "b200rs_event_synchronize")
+                    else:
+                        done = ctypes.c_int(0)
+                        check(lib().b200rs_event_query(self.handle, st["event"], ctypes.byref(done)), "b200rs_event_query")
+                        if not done.value:
+                            continue
+                    st["in_flight"] = False
+                if nbytes > st["bytes"]:
+                    if st["ptr"]:
+                        check(lib().b200rs_host_free(self.handle, ctypes.c_void_p(st["ptr"])), "b200rs_host_free")
+                    p = ctypes.c_void_p()
+                    check(lib().b200rs_host_alloc(self.handle, nbytes, ctypes.byref(p)), "b200rs_host_alloc")
+                    st["ptr"], st["bytes"] = int(p.value), nbytes
+                st["mapped"] = True
+                return i, st["ptr"]
+        raise RuntimeError("more than two buffers mapped at once")
+
+    def _release_stage(self, slot: int, copy_enqueued: bool) -> None:
+        st = self._stages[slot]
+        st["mapped"] = False
+        if copy_enqueued:
+            if st["event"] is None:
+                e = ctypes.c_void_p()
+                check(lib().b200rs_event_create(self.handle, ctypes.byref(e)), "b200rs_event_create")
+                st["event"] = e
+            check(lib().b200rs_event_record(self.handle, st["event"]), "b200rs_event_record")
+            st["in_flight"] = True
 
     @property
     def handle(self):
@@ -74,6 +112,13 @@ class Device:
 
     def release(self) -> None:
         if self._h:
+            lib().b200rs_device_sync(self._h)
+            for st in self._stages:
+                if st["ptr"]:
+                    lib().b200rs_host_free(self._h, ctypes.c_void_p(st["ptr"]))
+                if st["event"] is not None:
+                    lib().b200rs_event_destroy(self._h, st["event"])
+                st.update(ptr=0, bytes=0, event=None, mapped=False, in_flight=False)
             check(lib().b200rs_device_destroy(self._h), "b200rs_device_destroy")
             self._h = _lib.c_dev()
 
@@ -128,8 +173,11 @@ class Buffer:
         self.m_size = 0
         self.m_ptr = 0
         self.m_allocated = False
+        self._written = False  # contents defined on the device (see include/Adl/Adl.h: markDeviceWritten)
+        self._map = None
         if ptr is not None:
             self.m_ptr, self.m_size = int(ptr), int(nElems)
+            self._written = True
         elif nElems:
             self.allocate(nElems)
 
@@ -167,6 +215,7 @@ class Buffer:
         host = np.ascontiguousarray(host)
         n = host.shape[0] if nElems is None else nElems
         assert n + dstOffsetNElems <= self.m_size
+        self._written = True
         isz = self.dtype.itemsize
         check(lib().b200rs_memcpy_h2d(self.m_device.handle, ctypes.c_void_p(self.m_ptr + dstOffsetNElems * isz),
                                       ctypes.c_void_p(host.ctypes.data), n * isz), "b200rs_memcpy_h2d")
@@ -181,9 +230,28 @@ class Buffer:
         self.m_device.waitForCompletion()
         return out
 
-    # map/unmap semantics of the CL backend (AdlCL.inl:544-565): read+write host view
+    def markDeviceWritten(self) -> None:
+        self._written = True
+
+    # map/unmap semantics of the CL backend (AdlCL.inl:544-565): a read+write host view in pinned memory.  The copy out is
+    # stream-ordered (wait before reading, as with the reference's non-blocking map; skipped for a buffer nothing was ever
+    # written to), returnHostPtr enqueues the copy back and returns (the pinned block is recycled once it has passed).
     def getHostPtr(self, size: int | None = None) -> np.ndarray:
-        return self.read(self.m_size if size is None or size < 0 else size)
+        n = self.m_size if size is None or size < 0 or size > self.m_size else size
+        assert self._map is None, "one mapping at a time per buffer"
+        nbytes = n * self.dtype.itemsize
+        slot, addr = self.m_device._acquire_stage(max(nbytes, 1))
+        view = np.ctypeslib.as_array(ctypes.cast(ctypes.c_void_p(addr), ctypes.POINTER(ctypes.c_uint8)), shape=(nbytes,)).view(self.dtype)
+        if self._written and n:
+            check(lib().b200rs_memcpy_d2h(self.m_device.handle, ctypes.c_void_p(addr), ctypes.c_void_p(self.m_ptr), nbytes), "b200rs_memcpy_d2h")
+        self._map = (slot, addr, n)
+        return view
 
     def returnHostPtr(self, host: np.ndarray) -> None:
-        self.write(host, host.shape[0])
+        assert self._map is not None and host.ctypes.data == self._map[1], "not the view getHostPtr returned"
+        slot, addr, n = self._map
+        if n:
+            check(lib().b200rs_memcpy_h2d(self.m_device.handle, ctypes.c_void_p(self.m_ptr), ctypes.c_void_p(addr), n * self.dtype.itemsize), "b200rs_memcpy_h2d")
+        self._written = True
+        self.m_device._release_stage(slot, bool(n))
+        self._map = None

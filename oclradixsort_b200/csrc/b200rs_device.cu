@@ -100,6 +100,9 @@ int b200rs_device_destroy(b200rs_device* dev) {
         if (dev->ev_out[i]) cudaEventDestroy(dev->ev_out[i]);
     }
     if (dev->ev_start) cudaEventDestroy(dev->ev_start);
+    if (dev->ev_aux[0]) cudaEventDestroy(dev->ev_aux[0]);
+    if (dev->ev_aux[1]) cudaEventDestroy(dev->ev_aux[1]);
+    if (dev->aux) cudaStreamDestroy(dev->aux);
     if (dev->copy_in) cudaStreamDestroy(dev->copy_in);
     if (dev->copy_out) cudaStreamDestroy(dev->copy_out);
     if (dev->owns_stream && dev->stream) cudaStreamDestroy(dev->stream);

@@ -39,6 +39,10 @@ struct b200rs_device {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_sorted[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_start = nullptr;
 
+    // second stream of the partitioned sort (histograms next to the exchange kernel), created on first use
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_aux[2] = {nullptr, nullptr};
+
     bool profiling = false;
     std::vector<b200rs_profile_span> spans;
 

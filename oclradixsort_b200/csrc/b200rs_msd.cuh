@@ -347,17 +347,23 @@ msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out
     // ---- a tile whose keys all share the digit (presorted / reversed input: every tile but the ones on bucket edges) is
     //      copied straight from the registers, in input order, behind ONE cursor atomic ----
     {
-        uint32_t k_or = key[0][0], k_and = key[0][0];
-#pragma unroll
-        for (int v = 0; v < VPT; ++v)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { k_or |= key[v][c]; k_and &= key[v][c]; }
-        const uint32_t mine = __byte_perm(k_or, 0u, prmt_sel);
-        const bool uniform = full && __byte_perm(k_or ^ k_and, 0u, prmt_sel) == 0;  // this thread's keys share the digit
+        // cheap first: only if every thread's FIRST vector already agrees with thread 0's digit are all the keys looked at
+        const uint32_t mine = __byte_perm(key[0][0], 0u, prmt_sel);
         if (tid == 0) s.overflow = mine;
         __syncthreads();
         const uint32_t dtile = s.overflow;
-        const int one_digit = __syncthreads_and(uniform && mine == dtile);
+        const bool first_ok = full && __byte_perm((key[0][0] ^ key[0][1]) | (key[0][0] ^ key[0][2]) | (key[0][0] ^ key[0][3]), 0u, prmt_sel) == 0 && mine == dtile;
+        bool uniform = false;
+        const int all_first = __syncthreads_and(first_ok);  // CTA-uniform
+        if (all_first) {
+            uint32_t k_or = key[0][0], k_and = key[0][0];
+#pragma unroll
+            for (int v = 0; v < VPT; ++v)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { k_or |= key[v][c]; k_and &= key[v][c]; }
+            uniform = __byte_perm(k_or ^ k_and, 0u, prmt_sel) == 0;  // this thread's keys share the digit (and it is thread 0's)
+        }
+        const int one_digit = all_first ? __syncthreads_and(uniform) : 0;
         if (one_digit) {
             if (tid == 0) s.cnt2[0] = atomicAdd(&cursor[dtile], (uint32_t)Cfg::TILE);
             __syncthreads();

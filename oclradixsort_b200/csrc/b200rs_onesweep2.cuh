@@ -330,8 +330,10 @@ onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t
                  uint32_t pf_tiles /* L2 prefetch distance in tiles (about the number of co-resident CTAs); 0 = off */) {
     using Cfg = Onesweep2Config<ElemT, THREADS, IPT, WO>;
     static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(smem_raw);
+    // (own symbol: the other kernel families of this translation unit declare their dynamic shared memory with 16-byte
+    // alignment, and the swizzled body needs the staged tile on a 128-byte boundary)
+    extern __shared__ __align__(128) unsigned char os2_smem_raw[];
+    typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(os2_smem_raw);
     // Thread 0 fetches, concurrently, the tile ticket, the pass control word (digit_start_kernel: PASS_IDENTITY = every
     // element has the same digit in this pass, so the pass moves nothing) and the device-side element count (multi-GPU
     // sort): one L2 round trip for all three.

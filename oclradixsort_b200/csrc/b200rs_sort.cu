@@ -1054,7 +1054,8 @@ int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, c
 
 template <typename ElemT>
 int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes, const char* what,
-              const unsigned long long* n_dev = nullptr, int msd_mode = MSD_AUTO, int* msd_used = nullptr) {
+              const unsigned long long* n_dev = nullptr, int msd_mode = MSD_AUTO, int* msd_used = nullptr,
+              const unsigned long long* pre_hist = nullptr /* device, [passes][256] digit counts of the input: the histogram launch is skipped */) {
     if (!dev || !temp_bytes) return B200RS_ERR_INVALID_ARGUMENT;
     if (msd_used) *msd_used = 0;
     SortPlan plan;
@@ -1069,7 +1070,7 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     if (n <= 1 || plan.passes == 0) return B200RS_OK;  // nothing to order
 
     b200rs_device_guard guard(dev);
-    if (n <= (uint64_t)SMALL_CAP && !n_dev && msd_mode != MSD_FORCED && !b200rs_exp_env("B200RS_NO_SMALL_PATH", 0)) {
+    if (n <= (uint64_t)SMALL_CAP && !n_dev && !pre_hist && msd_mode != MSD_FORCED && !b200rs_exp_env("B200RS_NO_SMALL_PATH", 0)) {
         // one launch of one CTA: all passes in shared memory (no histogram, no tickets, no look-back, no temp storage)
         char small_label[48];
         snprintf(small_label, sizeof(small_label), "small_sort_%s", what);
@@ -1110,8 +1111,10 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
     uint32_t* pass_ctl = tickets + 32;  // [passes], inside the zeroed ticket block
     // generation >= 2 kernels need the pre-scanned histograms + pass control words: the aligned histogram kernels do that in
     // their last CTA (fused_digit_start); only the unaligned fallback still needs the separate digit_start launch
-    uint32_t* done_counter = var.gen >= 2 && ((uintptr_t)inout & 15u) == 0 ? tickets + 48 : nullptr;
-    {
+    uint32_t* done_counter = var.gen >= 2 && ((uintptr_t)inout & 15u) == 0 && !pre_hist ? tickets + 48 : nullptr;
+    if (pre_hist) {
+        B200RS_CUDA(cudaMemcpyAsync(ghist, pre_hist, sizeof(unsigned long long) * (size_t)plan.passes * RADIX, cudaMemcpyDeviceToDevice, dev->stream));
+    } else {
         snprintf(label, sizeof(label), "digit_histogram_%s", what);
         b200rs_launch_scope scope(dev, label, n, n * sizeof(ElemT));
         const uint64_t per_block = (uint64_t)HIST_THREADS * HIST_VEC_PER_THREAD * (16 / sizeof(ElemT));
@@ -1478,6 +1481,66 @@ exchange_partition_kernel(const uint2* __restrict__ in, uint64_t n, int shift, u
     (void)minus_one;
 }
 
+// ---- histograms of the local sort, taken on the SENDING side while the exchange runs ---------------------------------
+// The receiver's local sort starts with a histogram of all four digits of what it received (0.33 ms for 2^28 pairs).  The
+// sender reads every pair it ships anyway and the exchange kernel is bound by NVLink, not by the SM: this kernel runs next
+// to it (second stream) and counts, per destination, digits 0..2 of the pairs going there.  The tables are all-gathered
+// (world x parts x 3 x 256 counters) and every rank adds up its own column; digit 3 comes from the top-digit histograms
+// that were gathered for the plan.
+constexpr int DH_THREADS = 512, DH_DIGITS = 3;
+__global__ void __launch_bounds__(DH_THREADS)
+dest_digit_histogram_kernel(const uint2* __restrict__ in, uint64_t n, const unsigned long long* __restrict__ n_dev, const uint8_t* __restrict__ digit_lut,
+                            int parts, unsigned long long* __restrict__ out /*[parts][DH_DIGITS][RADIX], zeroed*/) {
+    extern __shared__ uint32_t dh_hist[];  // [parts][DH_DIGITS][RADIX]
+    __shared__ uint8_t s_lut[RADIX];
+    if (n_dev) n = min(n, (uint64_t)*n_dev);
+    const int cells = parts * DH_DIGITS * RADIX;
+    for (int i = threadIdx.x; i < cells; i += DH_THREADS) dh_hist[i] = 0;
+    if (threadIdx.x < RADIX) s_lut[threadIdx.x] = digit_lut[threadIdx.x];
+    __syncthreads();
+    const uint32_t table = smem_addr(dh_hist);
+    const uint64_t nvec = n / 2;  // two pairs per 128-bit load
+    const uint4* in4 = reinterpret_cast<const uint4*>(in);
+    const uint64_t stride = (uint64_t)gridDim.x * DH_THREADS;
+    auto count = [&](uint32_t key) {
+        const uint32_t base = table + (uint32_t)s_lut[key >> 24] * (DH_DIGITS * RADIX * 4u);
+        red_add_shared(base + 4u * (key & 255u), 1u);
+        red_add_shared(base + 4u * (RADIX + ((key >> 8) & 255u)), 1u);
+        red_add_shared(base + 4u * (2 * RADIX + ((key >> 16) & 255u)), 1u);
+    };
+    uint64_t v = (uint64_t)blockIdx.x * DH_THREADS + threadIdx.x;
+    for (; v + stride < nvec; v += 2 * stride) {
+        const uint4 a = __ldg(in4 + v), b = __ldg(in4 + v + stride);
+        count(a.x); count(a.z); count(b.x); count(b.z);
+    }
+    for (; v < nvec; v += stride) {
+        const uint4 a = __ldg(in4 + v);
+        count(a.x); count(a.z);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) count(in[n - 1].x);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cells; i += DH_THREADS)
+        if (dh_hist[i]) atomicAdd(&out[i], (unsigned long long)dh_hist[i]);
+}
+
+// ghist[p][d] of the local sort (4 x 256 u64): digits 0..2 = sum over sources of their tables' column `me`; digit 3 = the
+// gathered top-digit histograms, restricted to the digits this rank owns.
+__global__ void __launch_bounds__(RADIX)
+recv_histogram_kernel(const unsigned long long* __restrict__ tables /*[world][parts][DH_DIGITS][RADIX]*/, const unsigned long long* __restrict__ top_all /*[world][RADIX]*/,
+                      const uint8_t* __restrict__ digit_lut, int world, int me, const uint32_t* __restrict__ status, unsigned long long* __restrict__ ghist /*[4][RADIX]*/) {
+    const int d = threadIdx.x;
+    const bool aborted = status[0] != 0;
+    for (int p = 0; p < DH_DIGITS; ++p) {
+        unsigned long long sum = 0;
+        for (int s = 0; s < world; ++s) sum += tables[(((size_t)s * world + me) * DH_DIGITS + p) * RADIX + d];
+        ghist[p * RADIX + d] = aborted ? 0ull : sum;
+    }
+    unsigned long long top = 0;
+    if (digit_lut[d] == me)
+        for (int s = 0; s < world; ++s) top += top_all[(size_t)s * RADIX + d];
+    ghist[DH_DIGITS * RADIX + d] = aborted ? 0ull : top;
+}
+
 // ---- on-device exchange plan (one CTA of 256 threads): keeps the multi-GPU sort free of host round trips ----
 // hist_all[s][b] = pairs on source rank s with top digit b.  Digit ranges are contiguous per destination; the edge
 // between rank r-1 and r is the digit boundary whose cumulative count is closest to r*N/P (exact integer compare,
@@ -1668,18 +1731,28 @@ extern "C" int b200rs_sort_pairs_u32_devn(b200rs_device* dev, b200rs_pair* inout
                             reinterpret_cast<const unsigned long long*>(n_dev));
 }
 
+namespace {
+int sort_pairs_devn_with_histogram(b200rs_device* dev, b200rs_pair* inout, uint64_t n_max, const uint64_t* n_dev, const uint64_t* hist4x256, void* temp,
+                                   size_t* temp_bytes) {
+    return sort_impl<uint2>(dev, reinterpret_cast<uint2*>(inout), n_max, 32, temp, temp_bytes, "pairs", reinterpret_cast<const unsigned long long*>(n_dev),
+                            MSD_AUTO, nullptr, reinterpret_cast<const unsigned long long*>(hist4x256));
+}
+}  // namespace
+
 // ---- the whole partitioned sort of one rank (see include/b200rs.h) -------------------------------------------------------
 extern "C" int b200rs_dist_sort_pairs_u32(b200rs_device* dev, const b200rs_dist_comm* comm, const uint64_t* recv_base, uint64_t recv_capacity_pairs,
                                           const b200rs_pair* in, uint64_t n, uint64_t* counts_dev, uint32_t* status_dev, void* temp, size_t* temp_bytes) {
     if (!dev || !comm || !temp_bytes || comm->world < 1 || comm->world > XP_MAX_PARTS || comm->rank < 0 || comm->rank >= comm->world) return B200RS_ERR_INVALID_ARGUMENT;
     const int world = comm->world;
-    // temp: [own histogram 256 x u64][gathered world x 256 x u64][peer bases 256 x u64][part bases 256 x u64][lut 256][exchange temp][local sort temp]
+    // temp: [own top histogram 256 x u64][gathered world x 256 x u64][peer bases 256 x u64][part bases 256 x u64][lut 256]
+    //       [own destination tables world x 3 x 256 x u64][gathered world x that][histograms of the local sort 4 x 256 x u64][exchange temp][local sort temp]
     size_t xp_bytes = 0, sort_bytes = 0;
     B200RS_TRY(b200rs_exchange_pairs(dev, nullptr, n, 24, 8, nullptr, nullptr, world, nullptr, nullptr, &xp_bytes));
     B200RS_TRY(b200rs_sort_pairs_u32_devn(dev, nullptr, recv_capacity_pairs, nullptr, 32, nullptr, &sort_bytes));
+    const size_t table_bytes = (size_t)world * DH_DIGITS * RADIX * 8;
     const size_t hist_off = 0, gathered_off = hist_off + RADIX * 8, peers_off = gathered_off + (size_t)world * RADIX * 8, parts_off = peers_off + RADIX * 8,
-                 lut_off = parts_off + RADIX * 8, xp_off = lut_off + 256, sort_off = xp_off + b200rs_align_up(xp_bytes, 256),
-                 need = sort_off + b200rs_align_up(sort_bytes, 256);
+                 lut_off = parts_off + RADIX * 8, table_off = lut_off + 256, tables_off = table_off + table_bytes, ghist_off = tables_off + world * table_bytes,
+                 xp_off = ghist_off + 4 * RADIX * 8, sort_off = xp_off + b200rs_align_up(xp_bytes, 256), need = sort_off + b200rs_align_up(sort_bytes, 256);
     if (!temp) {
         *temp_bytes = need;
         return B200RS_OK;
@@ -1693,7 +1766,16 @@ extern "C" int b200rs_dist_sort_pairs_u32(b200rs_device* dev, const b200rs_dist_
     uint64_t* peers = reinterpret_cast<uint64_t*>(base + peers_off);
     uint64_t* part_base = reinterpret_cast<uint64_t*>(base + parts_off);
     uint8_t* lut = reinterpret_cast<uint8_t*>(base + lut_off);
+    unsigned long long* table = reinterpret_cast<unsigned long long*>(base + table_off);
+    unsigned long long* tables = reinterpret_cast<unsigned long long*>(base + tables_off);
+    uint64_t* ghist = reinterpret_cast<uint64_t*>(base + ghist_off);
+    if (!dev->aux) {  // second stream + events for the histogram that runs next to the exchange
+        B200RS_CUDA(cudaStreamCreateWithFlags(&dev->aux, cudaStreamNonBlocking));
+        B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_aux[0], cudaEventDisableTiming));
+        B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_aux[1], cudaEventDisableTiming));
+    }
     B200RS_CUDA(cudaMemcpyAsync(peers, recv_base, (size_t)world * 8, cudaMemcpyHostToDevice, dev->stream));  // (pageable source: staged by the runtime before the call returns)
+    B200RS_CUDA(cudaMemsetAsync(table, 0, table_bytes, dev->stream));
     B200RS_TRY(b200rs_digit_histogram_pairs(dev, in, n, 24, 8, hist));
     // the all-gather also orders this step after every rank's previous local sort: nobody overwrites a receive buffer that is still being read
     {
@@ -1701,14 +1783,45 @@ extern "C" int b200rs_dist_sort_pairs_u32(b200rs_device* dev, const b200rs_dist_
         if (rc != 0) return rc;
     }
     B200RS_TRY(b200rs_dist_plan(dev, gathered, world, comm->rank, peers, recv_capacity_pairs, n, lut, part_base, counts_dev, status_dev));
+    // second stream: per-destination histograms of digits 0..2 of what this rank ships, hidden behind the exchange where that
+    // is bound by NVLink (from 4 ranks on: 3/4 and more of the pairs leave the GPU; with 2 ranks half of them stay and the two
+    // kernels compete for the SMs: measured 2.05 against 1.70 ms for the exchange, nothing gained)
+    const bool overlap = b200rs_exp_env("B200RS_DIST_OVERLAP", world >= 4 ? 1 : 0) != 0;
+    B200RS_CUDA(cudaEventRecord(dev->ev_aux[0], dev->stream));
+    B200RS_CUDA(cudaStreamWaitEvent(dev->aux, dev->ev_aux[0], 0));
+    if (n && overlap) {
+        dev->launches++;
+        const size_t smem = (size_t)world * DH_DIGITS * RADIX * sizeof(uint32_t);
+        B200RS_TRY(b200rs_kernel_setup(dev, (const void*)dest_digit_histogram_kernel, smem));
+        uint64_t blocks = (n / 2 + (uint64_t)DH_THREADS * 4 - 1) / ((uint64_t)DH_THREADS * 4);
+        if (blocks > (uint64_t)dev->num_sms) blocks = (uint64_t)dev->num_sms;
+        if (blocks == 0) blocks = 1;
+        dest_digit_histogram_kernel<<<(unsigned)blocks, DH_THREADS, smem, dev->aux>>>(reinterpret_cast<const uint2*>(in), n, reinterpret_cast<const unsigned long long*>(counts_dev),
+                                                                                     lut, world, table);
+        B200RS_CUDA(cudaGetLastError());
+    }
+    B200RS_CUDA(cudaEventRecord(dev->ev_aux[1], dev->aux));
     size_t have = xp_bytes;
     B200RS_TRY(b200rs_exchange_pairs(dev, in, n, 24, 8, lut, part_base, world, counts_dev, base + xp_off, &have));
+    B200RS_CUDA(cudaStreamWaitEvent(dev->stream, dev->ev_aux[1], 0));
+    if (overlap) {
+        const int rc = comm->allgather(comm->user, table, tables, table_bytes);
+        if (rc != 0) return rc;
+    }
     {
         const int rc = comm->barrier(comm->user);  // every rank's stores have landed before anyone sorts
         if (rc != 0) return rc;
     }
     have = sort_bytes;
-    return b200rs_sort_pairs_u32_devn(dev, reinterpret_cast<b200rs_pair*>(recv_base[comm->rank]), recv_capacity_pairs, counts_dev + 1, 32, base + sort_off, &have);
+    b200rs_pair* mine = reinterpret_cast<b200rs_pair*>(recv_base[comm->rank]);
+    if (!overlap) return b200rs_sort_pairs_u32_devn(dev, mine, recv_capacity_pairs, counts_dev + 1, 32, base + sort_off, &have);
+    {
+        b200rs_launch_scope scope(dev, "recv_histogram", 4 * RADIX, (uint64_t)world * table_bytes);
+        recv_histogram_kernel<<<1, RADIX, 0, dev->stream>>>(tables, reinterpret_cast<const unsigned long long*>(gathered), lut, world, comm->rank, status_dev,
+                                                            reinterpret_cast<unsigned long long*>(ghist));
+    }
+    B200RS_CUDA(cudaGetLastError());
+    return sort_pairs_devn_with_histogram(dev, mine, recv_capacity_pairs, counts_dev + 1, ghist, base + sort_off, &have);
 }
 
 extern "C" int b200rs_enable_peer_access(b200rs_device* dev, int peer_device_idx) {

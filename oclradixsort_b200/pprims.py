@@ -61,6 +61,7 @@ class Pprims:
         temp = self._scratch(device, need.value)
         have = ctypes.c_size_t(temp.getSize())
         check(fn(device.handle, ctypes.c_void_p(inout.m_ptr), n, sortBits, ctypes.c_void_p(temp.m_ptr), ctypes.byref(have)), name)
+        inout.markDeviceWritten()
 
     def scan(self, device: Device, dst: Buffer, src: Buffer, n: int, sumOut: bool = False):
         """Pprims::scan, Pprims.cpp:122-179.  With sumOut=True returns the total of all n inputs
@@ -80,6 +81,7 @@ class Pprims:
             total_ptr = ctypes.c_void_p(self._word.m_ptr)
         check(fn(device.handle, ctypes.c_void_p(dst.m_ptr), ctypes.c_void_p(src.m_ptr), n, total_ptr, ctypes.c_void_p(temp.m_ptr),
                  ctypes.byref(have)), "b200rs_exclusive_scan_u32")
+        dst.markDeviceWritten()
         if sumOut:
             return int(self._word.read(1)[0])
         return None
@@ -90,6 +92,7 @@ class Pprims:
         if device is None:
             raise ValueError("device == 0: there is no Host path (reference: the CPU loop of Pprims.cpp:34-38)")
         assert n <= dst.getSize() and n <= src.getSize() and dst.dtype.itemsize == src.dtype.itemsize
+        dst.markDeviceWritten()
         if dst.dtype.itemsize == 4:
             check(lib().b200rs_copy_u32(device.handle, ctypes.c_void_p(dst.m_ptr), ctypes.c_void_p(src.m_ptr), n), "b200rs_copy_u32")
         elif dst.dtype.itemsize == 16:
@@ -103,6 +106,7 @@ class Pprims:
         if device is None:
             raise ValueError("device == 0: there is no Host path (reference: the CPU loop of Pprims.cpp:69-73)")
         assert n <= dst.getSize()
+        dst.markDeviceWritten()
         if dst.dtype.itemsize == 4:
             word = int(np.asarray(value, dtype=dst.dtype).view(np.uint32)) if dst.dtype.kind != "u" else int(value) & 0xFFFFFFFF
             check(lib().b200rs_fill_u32(device.handle, ctypes.c_void_p(dst.m_ptr), word, n), "b200rs_fill_u32")

@@ -117,3 +117,31 @@ def test_cpp_dropin_prims_stopwatch_profile_csv(tmp_path):
     rows = open(tmp_path / "gpurun_out_profile_test.csv").read().strip().splitlines()
     assert len(rows) >= 8 and rows[0].startswith('"digit_histogram_keys"'), rows[:3]
     assert all(len(r.split(",")) == 5 for r in rows)
+
+
+def test_buffer_map_unmap_pinned_ring():
+    """adl.Buffer.getHostPtr / returnHostPtr (the reference caller's sequence, UnitTest/main.cpp:118-139) through the pinned
+    staging ring: a fresh buffer is mapped without a copy, unmap does not block, two buffers filled back to back keep their
+    contents, the sorted result comes back through a second mapping."""
+    import oclradixsort_b200 as ob
+    from oracle import pyoracle as po
+    d = ob.DeviceUtils.allocate(ob.TYPE_CL)
+    p = ob.Pprims()
+    n = 300007
+    rng = np.random.default_rng(2)
+    keys = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    a, b = ob.Buffer(d, n, np.uint32), ob.Buffer(d, n, np.uint32)
+    m = a.getHostPtr(n)          # never written: no device -> host copy, the view can be filled at once
+    m[:] = keys
+    a.returnHostPtr(m)           # returns without waiting
+    m2 = b.getHostPtr(n)         # must not be the block the copy above is still reading
+    m2[:] = keys[::-1]
+    b.returnHostPtr(m2)
+    p.radixSort(d, a, n)
+    m = a.getHostPtr(n)
+    d.waitForCompletion()
+    assert np.array_equal(m, po.sort_u32(keys))
+    a.returnHostPtr(m)
+    assert np.array_equal(b.read(), keys[::-1])
+    a.release(); b.release(); p.release()
+    ob.DeviceUtils.deallocate(d)
