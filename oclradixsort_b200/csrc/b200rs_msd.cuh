@@ -271,6 +271,8 @@ msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out
             bulk_prefetch_l2(in + p.start, bytes);
         }
     } else {
+        // P1 is launched before the host has read the verdict of H + PL (it runs while the host waits): it checks for itself
+        if (ctl[MSD_CTL_INELIGIBLE]) return;
         start = blockIdx.x * (uint32_t)Cfg::TILE;
         count = min((uint32_t)Cfg::TILE, n - start);
         if (tid == 32 && pf_tiles) {

@@ -318,6 +318,14 @@ __device__ __forceinline__ void onesweep2_tile(typename Onesweep2Config<ElemT, T
     }
 }
 
+// (DSWZ == 2) the swizzled tile body as a separate function: its register allocation and spills stay out of the plain bodies
+template <typename ElemT, int THREADS, int IPT, int WO, int ORDER, int LOAD>
+__device__ __noinline__ void onesweep2_tile_regular(typename Onesweep2Config<ElemT, THREADS, IPT, WO>::Smem& s, const ElemT* __restrict__ in, ElemT* __restrict__ out,
+                                                    uint64_t tile_base, uint32_t valid, int shift, uint32_t digit_mask, uint32_t prmt_sel, uint32_t tile, uint32_t pass,
+                                                    const unsigned long long* __restrict__ digit_start, Lookback3 lb, uint32_t minus_one, bool in_aligned) {
+    onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, true, true, 1>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, in_aligned);
+}
+
 // DSWZ: the swizzled body is compiled in next to the plain one and taken (CTA-uniform branch, like the identity-pass test)
 // only in passes that digit_start flagged PASS_REGULAR -- presorted / reversed / strided keys, or a shuffled permutation of
 // a full range -- so inputs with ordinary histograms never pay for the swizzle's 7 + 4 extra instructions per element.
@@ -387,7 +395,9 @@ onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t
     const bool byte_digit = digit_mask == (uint32_t)(RADIX - 1);
     const uint32_t prmt_sel = 0x4440u | (uint32_t)(shift >> 3);
 
-    if (DSWZ && valid == Cfg::TILE && byte_digit && (s.ctl & PASS_REGULAR)) {
+    if (DSWZ == 2 && valid == Cfg::TILE && byte_digit && (s.ctl & PASS_REGULAR)) {
+        onesweep2_tile_regular<ElemT, THREADS, IPT, WO, ORDER, LOAD>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, in_aligned);
+    } else if (DSWZ == 1 && valid == Cfg::TILE && byte_digit && (s.ctl & PASS_REGULAR)) {
         onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, true, true, 1>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, in_aligned);
     } else if (valid == Cfg::TILE) {
         if (byte_digit) onesweep2_tile<ElemT, THREADS, IPT, WO, ORDER, LOAD, true, true, SWZ>(s, in, out, tile_base, valid, shift, digit_mask, prmt_sel, tile, pass, digit_start, lb, minus_one, in_aligned);

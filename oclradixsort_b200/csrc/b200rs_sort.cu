@@ -25,6 +25,8 @@
 // zeroed once per sort, serves every pass and counts never overflow (n up to 2^56).
 #include "b200rs_internal.h"
 
+#include <cooperative_groups.h>
+
 namespace {
 
 constexpr int RADIX_BITS = 8;
@@ -697,6 +699,111 @@ small_sort_kernel(ElemT* __restrict__ inout, uint32_t n, int sort_bits, uint32_t
     for (uint32_t j = tid; j < n; j += SMALL_THREADS) inout[j] = s.buf[cur][j];
 }
 
+// =================================================================================================
+// Mid-size inputs: the whole sort in ONE cooperative launch.
+// =================================================================================================
+// Between the single-CTA sort (<= 8192 elements) and inputs that fill the GPU, the multi-kernel chain is pure latency: memset,
+// histogram and one launch per digit, each a few microseconds of work behind a few microseconds of launch (44-48 us for any
+// n from 16K to 512K; the reference's own unit test sweeps 1K .. 1M, UnitTest/main.cpp:105).  Here one grid of co-resident
+// CTAs (cooperative launch) does everything, with grid-wide barriers where the chain had launches: clear the scratch,
+// histogram of all digits, digit starts (every CTA scans the four 256-bin histograms for itself: no barrier for that), then
+// one pass per digit -- the same tile body as the scatter kernel (onesweep2_tile, 2048-element tiles), tile k of CTA c is
+// tile c + k * grid, so a tile only waits on tiles of CTAs that are resident and move forward.
+constexpr int MIDC_THREADS = 256, MIDC_IPT = 8;
+template <typename ElemT>
+struct MidSortSmem {
+    typename Onesweep2Config<ElemT, MIDC_THREADS, MIDC_IPT, WO_ELEM>::Smem tile;
+    unsigned long long start[MAX_PASSES][RADIX];  // digit starts of every pass (exclusive scans of the histograms)
+    uint32_t hist[MAX_PASSES][RADIX];
+    uint64_t scratch[RADIX / 32];
+    uint32_t identity[MAX_PASSES];
+};
+
+template <typename ElemT>
+__global__ void __launch_bounds__(MIDC_THREADS, 4)
+mid_sort_kernel(ElemT* __restrict__ inout, ElemT* __restrict__ alt, uint32_t n, int sort_bits, unsigned long long* __restrict__ ghist /*[MAX_PASSES][RADIX]*/,
+                uint32_t* __restrict__ lb_partial, uint64_t* __restrict__ lb_group, uint32_t num_tiles, uint32_t minus_one) {
+    namespace cg = cooperative_groups;
+    using Cfg = Onesweep2Config<ElemT, MIDC_THREADS, MIDC_IPT, WO_ELEM>;
+    extern __shared__ __align__(128) unsigned char midc_smem_raw[];
+    MidSortSmem<ElemT>& s = *reinterpret_cast<MidSortSmem<ElemT>*>(midc_smem_raw);
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x;
+    const int passes = (sort_bits + RADIX_BITS - 1) / RADIX_BITS;
+    const uint32_t key_mask = sort_bits == 32 ? 0xffffffffu : ((1u << sort_bits) - 1u);
+
+    // ---- clear the look-back tables and the global histograms ----
+    const uint32_t num_groups = (num_tiles + LB_GROUP - 1) / LB_GROUP;
+    for (uint32_t i = blockIdx.x * MIDC_THREADS + tid; i < num_tiles * RADIX; i += gridDim.x * MIDC_THREADS) lb_partial[i] = 0;
+    for (uint32_t i = blockIdx.x * MIDC_THREADS + tid; i < num_groups * RADIX; i += gridDim.x * MIDC_THREADS) lb_group[i] = 0;
+    if (blockIdx.x == 0)
+        for (int i = tid; i < MAX_PASSES * RADIX; i += MIDC_THREADS) ghist[i] = 0;
+    for (int i = tid; i < MAX_PASSES * RADIX; i += MIDC_THREADS) (&s.hist[0][0])[i] = 0;
+    grid.sync();
+
+    // ---- histogram of every digit ----
+    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const uint32_t base = t * Cfg::TILE;
+#pragma unroll
+        for (int i = 0; i < MIDC_IPT; ++i) {
+            const uint32_t j = base + i * MIDC_THREADS + tid;
+            if (j < n) {
+                const uint32_t key = Elem<ElemT>::key(inout[j]) & key_mask;
+#pragma unroll
+                for (int p = 0; p < MAX_PASSES; ++p)
+                    if (p < passes) atomicAdd(&s.hist[p][(key >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < passes * RADIX; i += MIDC_THREADS) {
+        const uint32_t c = (&s.hist[0][0])[i];
+        if (c) atomicAdd(&ghist[i], (unsigned long long)c);
+    }
+    grid.sync();
+
+    // ---- digit starts and identity flags, computed by every CTA for itself ----
+    for (int p = 0; p < passes; ++p) {
+        const unsigned long long x = __ldcg(&ghist[p * RADIX + tid]);
+        const int degenerate = __syncthreads_or(x == (unsigned long long)n);
+        s.start[p][tid] = block_exclusive_scan_256<uint64_t>(x, s.scratch, tid);
+        if (tid == 0) s.identity[p] = degenerate ? 1u : 0u;
+    }
+    __syncthreads();
+
+    // ---- one pass per digit ----
+    Lookback3 lb;
+    lb.partial = lb_partial;
+    lb.group = lb_group;
+    ElemT* src = inout;
+    ElemT* dst = alt;
+    int moved = 0;
+    for (int p = 0; p < passes; ++p) {
+        if (s.identity[p]) continue;  // every element has the same digit: the pass would move nothing (CTA-uniform, same in every CTA)
+        const int shift = p * RADIX_BITS;
+        const int width = sort_bits - shift < RADIX_BITS ? sort_bits - shift : RADIX_BITS;
+        const uint32_t digit_mask = (1u << width) - 1u;
+        const uint32_t prmt_sel = 0x4440u | (uint32_t)(shift >> 3);
+        for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+#pragma unroll
+            for (int i = tid; i < Cfg::WARPS * RADIX; i += MIDC_THREADS) (&s.tile.warp_offset[0][0])[i] = 0;
+            __syncthreads();
+            const uint64_t tile_base = (uint64_t)t * Cfg::TILE;
+            const uint32_t valid = min((uint32_t)Cfg::TILE, n - (uint32_t)tile_base);
+            if (valid == Cfg::TILE && digit_mask == (uint32_t)(RADIX - 1))
+                onesweep2_tile<ElemT, MIDC_THREADS, MIDC_IPT, WO_ELEM, ORDER_LATE, LOAD_LDG, true, true, 0>(s.tile, src, dst, tile_base, valid, shift, digit_mask, prmt_sel, t, (uint32_t)p, s.start[p], lb, minus_one, false);
+            else
+                onesweep2_tile<ElemT, MIDC_THREADS, MIDC_IPT, WO_ELEM, ORDER_LATE, LOAD_LDG, false, false, 0>(s.tile, src, dst, tile_base, valid, shift, digit_mask, prmt_sel, t, (uint32_t)p, s.start[p], lb, minus_one, false);
+            __syncthreads();  // the tile body's shared memory is reused by the next tile
+        }
+        ElemT* tmp = src; src = dst; dst = tmp;
+        ++moved;
+        grid.sync();  // pass p + 1 reads what every CTA wrote in pass p
+    }
+    if (moved & 1)  // the result sits in the alternate buffer
+        for (uint32_t j = blockIdx.x * MIDC_THREADS + tid; j < n; j += gridDim.x * MIDC_THREADS) inout[j] = src[j];
+}
+
 // ---- host side -------------------------------------------------------------------------------------
 
 // Scatter-pass kernels.  The production library contains exactly two per element type: the full-size tile and the 2048-element
@@ -720,6 +827,8 @@ struct Variant {
     Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO, ORDER, LOAD>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":" #WO ":" #ORDER ":" #LOAD, 2, 0}
 #define B200RS_VARIANT2D(ElemT, THREADS, IPT, MIN_CTAS) \
     Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO_ELEM, ORDER_LATE, LOAD_LDG, 0, 1>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO_ELEM>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":swizzled-when-regular", 2, 0}
+#define B200RS_VARIANT2N(ElemT, THREADS, IPT, MIN_CTAS) \
+    Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO_ELEM, ORDER_LATE, LOAD_LDG, 0, 2>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO_ELEM>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":swizzled-when-regular:noinline", 2, 0}
 #define B200RS_VARIANT2S(ElemT, THREADS, IPT, MIN_CTAS) \
     Variant{(const void*)onesweep2_kernel<ElemT, THREADS, IPT, MIN_CTAS, WO_ELEM, ORDER_LATE, LOAD_LDG, 1>, THREADS, IPT, sizeof(typename Onesweep2Config<ElemT, THREADS, IPT, WO_ELEM>::Smem), "v2:" #THREADS "x" #IPT "/" #MIN_CTAS ":swizzled", 2, 0}
 #define B200RS_VARIANT3(ElemT, THREADS, IPT, MIN_CTAS, PF) \
@@ -791,7 +900,17 @@ template <> struct Variants<uint32_t> {
 };
 template <> struct Variants<uint2> {
     // 320 threads x 20 pairs = 25 pairs per digit on average (odd, see the keys note), 3 CTAs/SM
-    static const Variant& full_size() { static const Variant v = B200RS_VARIANT2(uint2, 320, 20, 3, WO_ELEM, ORDER_LATE, LOAD_LDG); return v; }
+    // plus the swizzled body for passes flagged PASS_REGULAR, as a separate (noinline) function so that its registers and spills
+    // stay out of the plain bodies: presorted pairs 4.86 -> 3.91 ms, uniform 4.253 -> 4.258 (inlined: 4.285)
+    static const Variant& full_size() {
+        static const Variant v = B200RS_VARIANT2N(uint2, 320, 20, 3);
+#ifdef B200RS_EXPERIMENTS
+        static const Variant plain = B200RS_VARIANT2(uint2, 320, 20, 3, WO_ELEM, ORDER_LATE, LOAD_LDG), d1 = B200RS_VARIANT2D(uint2, 320, 20, 3);
+        const int i = b200rs_exp_env("B200RS_PAIRS_REGULAR", 2);
+        if (i != 2) return i == 1 ? d1 : plain;
+#endif
+        return v;
+    }
     static const Variant& mid_size() { static const Variant v = B200RS_VARIANT2(uint2, 256, 8, 4, WO_ELEM, ORDER_LATE, LOAD_LDG); return v; }  // 2048-pair tiles
 #if defined(B200RS_EXPERIMENTS) && B200RS_EXPERIMENTS >= 2
     static const Variant* list(int* count) {
@@ -842,9 +961,10 @@ template <> struct Variants<uint2> {
 // count, rank, look-back and write-out, on a mostly empty GPU (63 us for any n from 16K to 1M keys with the full-size tiles).
 // Small tiles put the same elements on 4 x as many SMs and make each chain 4 x shorter.
 constexpr uint64_t MID_N = 1ull << 19;  // measured: 2048-element tiles win up to 2^19 (44-48 us against 63), tie at 2^20
+constexpr uint64_t MIDC_MAX_N = 1ull << 20;  // up to here the sort is one cooperative launch (mid_sort_kernel): at most 512 tiles of 2048
 constexpr uint64_t MIN_TILE = 256 * 21;     // smallest tile among the variants used above MID_N: temp storage is sized for it
 constexpr uint64_t MIN_TILE_MID = 256 * 8;  // ... and up to MID_N
-inline uint64_t min_tile_for(uint64_t n) { return n <= MID_N ? MIN_TILE_MID : MIN_TILE; }
+inline uint64_t min_tile_for(uint64_t n) { return n <= MIDC_MAX_N ? MIN_TILE_MID : MIN_TILE; }  // (MIDC_MAX_N >= MID_N)
 
 template <typename ElemT>
 const Variant& pick_variant(uint64_t n) {
@@ -981,7 +1101,8 @@ constexpr uint32_t MSD_MAX_BUCKET = 256 * 48 - 31;
 
 // Returns B200RS_OK when the keys were sorted here, MSD_NOT_ELIGIBLE when the input is not eligible (the caller runs the LSD
 // path), an error code otherwise.  ONE host round trip: the choice between the two paths depends on the joint histogram, and both
-// paths are whole kernel chains, so the host waits for H + PL (about a tenth of the sort) and reads two words.
+// paths are whole kernel chains, so the host waits for H + PL (about a tenth of the sort) and reads two words -- with the first
+// partition pass already queued behind them, so the GPU is not idle meanwhile.
 constexpr int MSD_NOT_ELIGIBLE = -1000;
 int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, const SortPlan& plan) {
     if (((uintptr_t)inout & 15u) != 0 || b200rs_exp_env("B200RS_NO_MSD", 0)) return MSD_NOT_ELIGIBLE;
@@ -1012,13 +1133,12 @@ int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, c
         msd_plan_kernel<<<RADIX, RADIX, 0, dev->stream>>>(joint, hist3, n32, (uint32_t)ps.tile, MSD_MAX_BUCKET, bucket_off, cursor2, cursor1, tiles, ctl);
     }
     B200RS_CUDA(cudaGetLastError());
+    if (!dev->ev_msd) B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_msd, cudaEventDisableTiming));
     B200RS_CUDA(cudaMemcpyAsync(dev->pinned_word, ctl, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, dev->stream));
-    B200RS_CUDA(cudaStreamSynchronize(dev->stream));
-    if (dev->pinned_word[MSD_CTL_INELIGIBLE]) return MSD_NOT_ELIGIBLE;
-    const MsdBucketShape* fs = msd_bucket_shape(dev->pinned_word[MSD_CTL_MAX_BUCKET]);
-    if (!fs) return MSD_NOT_ELIGIBLE;
-    B200RS_TRY(b200rs_kernel_setup(dev, fs->kernel, fs->smem));
+    B200RS_CUDA(cudaEventRecord(dev->ev_msd, dev->stream));
 
+    // P1 goes out BEFORE the host waits: it reads the verdict itself (every CTA returns at once when the input is not eligible,
+    // ~15 us), so the host's round trip hides behind it instead of leaving the GPU idle (~14 us, profiles/r2a_launch_cost.txt)
     B200RS_TRY(b200rs_kernel_setup(dev, ps.p1, ps.smem));
     B200RS_TRY(b200rs_kernel_setup(dev, ps.p2, ps.smem));
     const uint32_t* in1 = inout;
@@ -1032,6 +1152,11 @@ int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, c
         void* args[] = {&in1, &alt, (void*)&n32, &shift1, &cursor1, &no_tiles, &ctl_c, &pf_tiles};
         B200RS_CUDA(cudaLaunchKernel(ps.p1, dim3((unsigned)((n + ps.tile - 1) / ps.tile)), dim3(ps.threads), args, ps.smem, dev->stream));
     }
+    B200RS_CUDA(cudaEventSynchronize(dev->ev_msd));
+    if (dev->pinned_word[MSD_CTL_INELIGIBLE]) return MSD_NOT_ELIGIBLE;
+    const MsdBucketShape* fs = msd_bucket_shape(dev->pinned_word[MSD_CTL_MAX_BUCKET]);
+    if (!fs) return MSD_NOT_ELIGIBLE;  // (cannot happen: PL marks buckets above MSD_MAX_BUCKET ineligible; P1 only wrote the temp buffer)
+    B200RS_TRY(b200rs_kernel_setup(dev, fs->kernel, fs->smem));
     {
         b200rs_launch_scope scope(dev, "msd_partition_keys_pass1", n, 8ull * n);
         const uint32_t* in2 = alt;
@@ -1084,6 +1209,29 @@ int sort_impl(b200rs_device* dev, ElemT* inout, uint64_t n, int sort_bits, void*
         return B200RS_OK;
     }
     char* base = static_cast<char*>(temp);
+    if (n <= MIDC_MAX_N && !n_dev && !pre_hist && msd_mode != MSD_FORCED && !b200rs_exp_env("B200RS_NO_COOP_MID", 0)) {
+        // one cooperative launch for the whole sort (see mid_sort_kernel); grid = what is co-resident, at most one CTA per tile
+        using MCfg = Onesweep2Config<ElemT, MIDC_THREADS, MIDC_IPT, WO_ELEM>;
+        const uint32_t tiles = (uint32_t)((n + MCfg::TILE - 1) / MCfg::TILE);
+        const size_t smem = sizeof(MidSortSmem<ElemT>);
+        int per_sm = 0;
+        B200RS_TRY(b200rs_kernel_setup(dev, (const void*)mid_sort_kernel<ElemT>, smem, MIDC_THREADS, &per_sm));
+        uint32_t grid = (uint32_t)(per_sm > 0 ? per_sm : 1) * (uint32_t)dev->num_sms;
+        if (grid > tiles) grid = tiles;
+        ElemT* alt = reinterpret_cast<ElemT*>(base + plan.alt_off);
+        unsigned long long* ghist = reinterpret_cast<unsigned long long*>(base + plan.hist_off);
+        uint32_t* lb_partial = reinterpret_cast<uint32_t*>(base + plan.lookback_off);
+        uint64_t* lb_group = reinterpret_cast<uint64_t*>(base + plan.lookback_off + b200rs_align_up((size_t)tiles * RADIX * sizeof(uint32_t), 256));
+        uint32_t n32 = (uint32_t)n, minus_one = 0xffffffffu, tiles_arg = tiles;
+        void* args[] = {&inout, &alt, &n32, &sort_bits, &ghist, &lb_partial, &lb_group, &tiles_arg, &minus_one};
+        char mid_label[48];
+        snprintf(mid_label, sizeof(mid_label), "mid_sort_%s", what);
+        {
+            b200rs_launch_scope scope(dev, mid_label, n, (uint64_t)(1 + 2 * plan.passes) * n * sizeof(ElemT));
+            B200RS_CUDA(cudaLaunchCooperativeKernel((const void*)mid_sort_kernel<ElemT>, dim3(grid), dim3(MIDC_THREADS), args, smem, dev->stream));
+        }
+        return B200RS_OK;
+    }
     if (plan.msd && !n_dev) {
         const int r = sort_keys_msd(dev, reinterpret_cast<uint32_t*>(inout), n, base, plan);
         if (r == B200RS_OK && msd_used) *msd_used = 1;
