@@ -102,7 +102,6 @@ int b200rs_device_destroy(b200rs_device* dev) {
     if (dev->ev_start) cudaEventDestroy(dev->ev_start);
     if (dev->ev_aux[0]) cudaEventDestroy(dev->ev_aux[0]);
     if (dev->ev_aux[1]) cudaEventDestroy(dev->ev_aux[1]);
-    if (dev->ev_msd) cudaEventDestroy(dev->ev_msd);
     if (dev->aux) cudaStreamDestroy(dev->aux);
     if (dev->copy_in) cudaStreamDestroy(dev->copy_in);
     if (dev->copy_out) cudaStreamDestroy(dev->copy_out);

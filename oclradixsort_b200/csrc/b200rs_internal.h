@@ -42,7 +42,6 @@ struct b200rs_device {
     // second stream of the partitioned sort (histograms next to the exchange kernel), created on first use
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev_msd = nullptr;  // recorded behind the 8-byte read-back of the key-only MSD path's verdict
 
     bool profiling = false;
     std::vector<b200rs_profile_span> spans;

@@ -38,6 +38,18 @@ enum MsdCtl {
     MSD_CTL_P2_TILES = 2,    // tiles of the second partition pass
     MSD_CTL_WORDS = 8,
 };
+// Programmatic dependent launch (the chain H -> PL -> PL -> P1 -> P2 -> F is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): a kernel of the chain does what needs no global data (zeroing its
+// shared memory), then WAITS for the previous grid to complete (griddepcontrol.wait: all of its memory operations are
+// visible), then lets the next grid's CTAs be scheduled as SMs drain.  Wait before release, in every CTA, so "the previous
+// grid completed" is transitive down the chain; every global access of a chain kernel sits behind its wait.  Both
+// instructions are no-ops in a kernel that was launched the ordinary way (profiling on; ncu).  About 5 us per kernel
+// boundary otherwise (profiles/r2a_launch_cost.txt).
+__device__ __forceinline__ void chain_wait_then_release() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 enum MsdIneligible {
     MSD_WHY_CHECKSUM = 1,  // a 16-bit counter of H wrapped
     MSD_WHY_BUCKET = 2,    // PL: a bucket is larger than F's capacity
@@ -53,8 +65,8 @@ enum MsdIneligible {
 // sum of all halves read back equals the number of keys the CTA counted unless some half wrapped (each wrap lowers it by
 // 65 535 or 65 536: wraps cannot cancel) -- and a wrap means a bucket beyond anything F can take, so the input is simply
 // marked ineligible.  A warp whose 128 keys (one LDG.128 each) share one bin -- presorted input -- adds them with one RED.
-constexpr int MSD_HIST_THREADS = 1024;
-constexpr int MSD_HIST_VECS = 4;  // LDG.128 in flight per thread
+constexpr int MSD_HIST_THREADS_DEFAULT = 1024;
+constexpr int MSD_HIST_VECS_DEFAULT = 8;  // LDG.128 in flight per thread (4: 0.190 ms at 2^28 keys, 6: 0.184, 8: 0.182; 512 threads x 8: 0.219)
 constexpr size_t MSD_HIST_SMEM = (size_t)(MSD_BUCKETS / 2) * sizeof(uint32_t);
 
 // Every MSD_HIST_CHECK_ROUNDS rounds the CTA looks for a counter above `bucket_cap`: its own share of one bucket already
@@ -62,7 +74,8 @@ constexpr size_t MSD_HIST_SMEM = (size_t)(MSD_BUCKETS / 2) * sizeof(uint32_t);
 // that hit the same counter are serialised -- and would be sent to the LSD path anyway).  The decision is local: the
 // CTAs see statistically the same data (grid-stride rounds), so they all stop within a check or two of each other,
 // and nobody waits for a global flag.
-constexpr int MSD_HIST_FIRST_CHECK = 8, MSD_HIST_CHECK_ROUNDS = 64;  // rounds (16 Ki keys per CTA each): one early look, then one per 1 Mi keys
+constexpr int MSD_HIST_FIRST_CHECK = 4, MSD_HIST_CHECK_ROUNDS = 32;  // rounds (32 Ki keys per CTA each): one early look, then one per 1 Mi keys
+template <int MSD_HIST_THREADS, int MSD_HIST_VECS>
 __global__ void __launch_bounds__(MSD_HIST_THREADS, 1)
 msd_hist16_kernel(const uint32_t* __restrict__ in, uint64_t n, unsigned long long* __restrict__ joint2 /*[32768] pairs of u32 counters*/,
                   uint32_t* __restrict__ ctl, uint32_t bucket_cap) {
@@ -70,6 +83,7 @@ msd_hist16_kernel(const uint32_t* __restrict__ in, uint64_t n, unsigned long lon
     __shared__ uint32_t s_sum[MSD_HIST_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < MSD_BUCKETS / 8; i += MSD_HIST_THREADS) reinterpret_cast<uint4*>(msd_tab)[i] = make_uint4(0, 0, 0, 0);
+    chain_wait_then_release();
     __syncthreads();
     const uint32_t table = smem_addr(msd_tab);
     uint32_t counted = 0;  // keys this thread added to the table
@@ -164,6 +178,7 @@ __global__ void __launch_bounds__(RADIX)
 msd_plan_sums_kernel(const uint32_t* __restrict__ joint, uint32_t* __restrict__ hist3 /*[256]*/, uint32_t* __restrict__ ctl) {
     __shared__ uint32_t s_sum[RADIX / 32], s_max[RADIX / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    chain_wait_then_release();
     const uint32_t x = __ldcg(joint + blockIdx.x * RADIX + tid);
     uint32_t sum = x, mx = x;
 #pragma unroll
@@ -189,11 +204,13 @@ msd_plan_kernel(const uint32_t* __restrict__ joint /*[65536]*/, const uint32_t* 
                 uint32_t* __restrict__ bucket_off /*[65537]: final start of every top-16 bucket*/,
                 uint32_t* __restrict__ cursor2 /*[65536]: = bucket_off, consumed by P2*/,
                 uint32_t* __restrict__ cursor1 /*[256]: start of every P1 bucket in the intermediate buffer, consumed by P1*/,
-                MsdTile* __restrict__ tiles, uint32_t* __restrict__ ctl) {
+                MsdTile* __restrict__ tiles, uint32_t* __restrict__ ctl,
+                volatile uint32_t* __restrict__ host_verdict /* pinned host memory: [1] = largest bucket, then [0] = why not eligible (0: eligible) */) {
     __shared__ uint32_t scratch[RADIX / 32];
     __shared__ uint32_t s_bcast[4];
     const int tid = threadIdx.x;
     const uint32_t b = blockIdx.x;
+    chain_wait_then_release();
     const uint32_t size3 = __ldcg(hist3 + tid);
     const uint32_t start3 = block_exclusive_scan_256<uint32_t>(size3, scratch, tid);          // final start of first-pass bucket tid
     const uint32_t t3 = (size3 + tile_keys - 1) / tile_keys;
@@ -203,7 +220,13 @@ msd_plan_kernel(const uint32_t* __restrict__ joint /*[65536]*/, const uint32_t* 
     if (b == 0 && tid == RADIX - 1) {
         ctl[MSD_CTL_P2_TILES] = tile_first + t3;
         bucket_off[MSD_BUCKETS] = n;
-        if (__ldcg(ctl + MSD_CTL_MAX_BUCKET) > bucket_cap) atomicOr(&ctl[MSD_CTL_INELIGIBLE], (uint32_t)MSD_WHY_BUCKET);
+        const uint32_t mx = __ldcg(ctl + MSD_CTL_MAX_BUCKET);
+        uint32_t why = __ldcg(ctl + MSD_CTL_INELIGIBLE);  // (H's verdicts: complete, H is two grids back)
+        if (mx > bucket_cap) { why |= (uint32_t)MSD_WHY_BUCKET; ctl[MSD_CTL_INELIGIBLE] = why; }
+        // the host is polling these two words (it picks the shape of F and decides between this pipeline and the LSD path)
+        host_verdict[1] = mx;
+        __threadfence_system();
+        host_verdict[0] = why;
     }
     __syncthreads();
     const uint32_t my_start = s_bcast[0], my_size = s_bcast[1], my_tile0 = s_bcast[2], my_tiles = s_bcast[3];
@@ -256,6 +279,9 @@ msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out
     typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(msd_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    for (int i = tid; i < RADIX; i += THREADS) s.cnt[i] = 0;
+    if (tid == 0) s.overflow = 0;
+    chain_wait_then_release();
     uint32_t start, count;
     if (SEGMENTED) {
         const uint32_t num_tiles = ctl[MSD_CTL_P2_TILES];
@@ -280,8 +306,6 @@ msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out
             if (p + Cfg::TILE <= n) bulk_prefetch_l2(in + p, (uint32_t)Cfg::TILE * 4u);
         }
     }
-    for (int i = tid; i < RADIX; i += THREADS) s.cnt[i] = 0;
-    if (tid == 0) s.overflow = 0;
 
     // ---- load: key (v, tid, c) of the tile is in[start + (v * THREADS + tid) * 4 + c] ----
     uint32_t key[VPT][4];
@@ -507,6 +531,12 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
     extern __shared__ __align__(16) unsigned char msd_smem_raw[];
     typename Cfg::Smem& s = *reinterpret_cast<typename Cfg::Smem*>(msd_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {   // zero the counters
+        uint4* z = reinterpret_cast<uint4*>(s.cnt);
+#pragma unroll
+        for (int i = 0; i < Cfg::WORDS / 4 / THREADS; ++i) z[i * THREADS + tid] = make_uint4(0, 0, 0, 0);
+    }
+    chain_wait_then_release();
     const uint32_t start = bucket_off[blockIdx.x];
     const uint32_t size = bucket_off[blockIdx.x + 1] - start;
     // the CTA that will take over this CTA's slot handles a bucket about pf_buckets further on: pull it into L2 now
@@ -521,11 +551,6 @@ msd_bucket_kernel(uint32_t* __restrict__ data, const uint32_t* __restrict__ buck
     uint32_t* __restrict__ keys = data + start;           // (robust route)
     uint32_t* __restrict__ window = data + start - lead;  // (never dereferenced below data + start)
 
-    {   // zero the counters
-        uint4* z = reinterpret_cast<uint4*>(s.cnt);
-#pragma unroll
-        for (int i = 0; i < Cfg::WORDS / 4 / THREADS; ++i) z[i * THREADS + tid] = make_uint4(0, 0, 0, 0);
-    }
     // this thread holds window slots tid, tid + THREADS, ...: the first `mine_n` of its IPT items, minus item 0 when
     // tid < lead
     const uint32_t wend = lead + size;

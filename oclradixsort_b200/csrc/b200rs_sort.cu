@@ -26,6 +26,7 @@
 #include "b200rs_internal.h"
 
 #include <cooperative_groups.h>
+#include <atomic>
 
 namespace {
 
@@ -1104,6 +1105,23 @@ constexpr uint32_t MSD_MAX_BUCKET = 256 * 48 - 31;
 // paths are whole kernel chains, so the host waits for H + PL (about a tenth of the sort) and reads two words -- with the first
 // partition pass already queued behind them, so the GPU is not idle meanwhile.
 constexpr int MSD_NOT_ELIGIBLE = -1000;
+// One launch of the chain.  `after_kernel`: the previous operation in the stream is a kernel of the chain, so this one may be
+// scheduled while that one drains (programmatic dependent launch; see chain_wait_then_release).  With profiling on there is
+// an event record between any two kernels and the attribute changes nothing.
+inline cudaError_t msd_launch(const void* kernel, unsigned grid, unsigned threads, size_t smem, cudaStream_t stream, void** args, bool after_kernel) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = after_kernel ? 1 : 0;
+    return cudaLaunchKernelExC(&cfg, kernel, args);
+}
+
 int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, const SortPlan& plan) {
     if (((uintptr_t)inout & 15u) != 0 || b200rs_exp_env("B200RS_NO_MSD", 0)) return MSD_NOT_ELIGIBLE;
     if (!dev->pinned_word) B200RS_CUDA(cudaHostAlloc((void**)&dev->pinned_word, 64, cudaHostAllocDefault));
@@ -1115,30 +1133,51 @@ int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, c
     uint32_t* cursor1 = reinterpret_cast<uint32_t*>(base + plan.msd_cursor1_off);
     MsdTile* tiles = reinterpret_cast<MsdTile*>(base + plan.msd_tiles_off);
     const MsdPartitionShape& ps = msd_partition_shape();
-    const uint32_t n32 = (uint32_t)n;
+    uint32_t n32 = (uint32_t)n;
+    const bool pdl = !b200rs_exp_env("B200RS_MSD_NO_PDL", 0);
+    // the verdict of H + PL arrives in two words of pinned host memory, written by the last plan kernel (no copy operation in
+    // the stream); [0] holds a value no verdict can take until then
+    constexpr uint32_t NO_VERDICT = 0xffffffffu;
+    volatile uint32_t* verdict = dev->pinned_word + 8;
+    verdict[0] = NO_VERDICT;
 
     B200RS_CUDA(cudaMemsetAsync(joint, 0, (size_t)MSD_BUCKETS * sizeof(uint32_t) + 256, dev->stream));  // joint histogram + control words
-    B200RS_TRY(b200rs_kernel_setup(dev, (const void*)msd_hist16_kernel, MSD_HIST_SMEM));
     {
+        struct HShape { const void* kernel; int threads, vecs; };
+        HShape h = {(const void*)msd_hist16_kernel<MSD_HIST_THREADS_DEFAULT, MSD_HIST_VECS_DEFAULT>, MSD_HIST_THREADS_DEFAULT, MSD_HIST_VECS_DEFAULT};
+#ifdef B200RS_EXPERIMENTS
+        static const HShape hs[] = {{(const void*)msd_hist16_kernel<1024, 8>, 1024, 8}, {(const void*)msd_hist16_kernel<1024, 2>, 1024, 2}, {(const void*)msd_hist16_kernel<1024, 4>, 1024, 4},
+                                    {(const void*)msd_hist16_kernel<512, 8>, 512, 8},   {(const void*)msd_hist16_kernel<768, 4>, 768, 4},   {(const void*)msd_hist16_kernel<1024, 6>, 1024, 6}};
+        const int hi = b200rs_exp_env("B200RS_MSD_H", 0);
+        if (hi >= 0 && hi < (int)(sizeof(hs) / sizeof(hs[0]))) h = hs[hi];
+#endif
+        B200RS_TRY(b200rs_kernel_setup(dev, h.kernel, MSD_HIST_SMEM));
         b200rs_launch_scope scope(dev, "msd_hist16_keys", n, n * 4ull);
-        const uint64_t per_block = (uint64_t)MSD_HIST_THREADS * MSD_HIST_VECS * 4;
+        const uint64_t per_block = (uint64_t)h.threads * h.vecs * 4;
         uint64_t blocks = (n + per_block - 1) / per_block;
         if (blocks > (uint64_t)dev->num_sms) blocks = (uint64_t)dev->num_sms;
-        msd_hist16_kernel<<<(unsigned)blocks, MSD_HIST_THREADS, MSD_HIST_SMEM, dev->stream>>>(inout, n, reinterpret_cast<unsigned long long*>(joint), ctl, MSD_MAX_BUCKET);
+        unsigned long long* joint2 = reinterpret_cast<unsigned long long*>(joint);
+        uint64_t n64 = n;
+        uint32_t cap = MSD_MAX_BUCKET;
+        void* args[] = {(void*)&inout, (void*)&n64, (void*)&joint2, (void*)&ctl, (void*)&cap};
+        B200RS_CUDA(msd_launch(h.kernel, (unsigned)blocks, (unsigned)h.threads, MSD_HIST_SMEM, dev->stream, args, false));
+    }
+    uint32_t* hist3 = cursor1 + RADIX;
+    {
+        b200rs_launch_scope scope(dev, "msd_plan_sums", MSD_BUCKETS, (uint64_t)MSD_BUCKETS * 4);
+        void* args[] = {(void*)&joint, (void*)&hist3, (void*)&ctl};
+        B200RS_CUDA(msd_launch((const void*)msd_plan_sums_kernel, RADIX, RADIX, 0, dev->stream, args, pdl));
     }
     {
-        uint32_t* hist3 = cursor1 + RADIX;
         b200rs_launch_scope scope(dev, "msd_plan", MSD_BUCKETS, (uint64_t)MSD_BUCKETS * 12);
-        msd_plan_sums_kernel<<<RADIX, RADIX, 0, dev->stream>>>(joint, hist3, ctl);
-        msd_plan_kernel<<<RADIX, RADIX, 0, dev->stream>>>(joint, hist3, n32, (uint32_t)ps.tile, MSD_MAX_BUCKET, bucket_off, cursor2, cursor1, tiles, ctl);
+        uint32_t tile_keys = (uint32_t)ps.tile, cap = MSD_MAX_BUCKET;
+        uint32_t* verdict_dev = dev->pinned_word + 8;  // (unified addressing: pinned host memory is addressable from the device as is)
+        void* args[] = {(void*)&joint, (void*)&hist3, (void*)&n32, (void*)&tile_keys, (void*)&cap, (void*)&bucket_off, (void*)&cursor2, (void*)&cursor1, (void*)&tiles, (void*)&ctl, (void*)&verdict_dev};
+        B200RS_CUDA(msd_launch((const void*)msd_plan_kernel, RADIX, RADIX, 0, dev->stream, args, pdl));
     }
-    B200RS_CUDA(cudaGetLastError());
-    if (!dev->ev_msd) B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_msd, cudaEventDisableTiming));
-    B200RS_CUDA(cudaMemcpyAsync(dev->pinned_word, ctl, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, dev->stream));
-    B200RS_CUDA(cudaEventRecord(dev->ev_msd, dev->stream));
 
-    // P1 goes out BEFORE the host waits: it reads the verdict itself (every CTA returns at once when the input is not eligible,
-    // ~15 us), so the host's round trip hides behind it instead of leaving the GPU idle (~14 us, profiles/r2a_launch_cost.txt)
+    // P1 goes out BEFORE the host has the verdict: it reads the verdict itself (every CTA returns at once when the input is not
+    // eligible, ~15 us), so the host's round trip hides behind it instead of leaving the GPU idle
     B200RS_TRY(b200rs_kernel_setup(dev, ps.p1, ps.smem));
     B200RS_TRY(b200rs_kernel_setup(dev, ps.p2, ps.smem));
     const uint32_t* in1 = inout;
@@ -1150,11 +1189,19 @@ int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, c
     {
         b200rs_launch_scope scope(dev, "msd_partition_keys_pass0", n, 8ull * n);
         void* args[] = {&in1, &alt, (void*)&n32, &shift1, &cursor1, &no_tiles, &ctl_c, &pf_tiles};
-        B200RS_CUDA(cudaLaunchKernel(ps.p1, dim3((unsigned)((n + ps.tile - 1) / ps.tile)), dim3(ps.threads), args, ps.smem, dev->stream));
+        B200RS_CUDA(msd_launch(ps.p1, (unsigned)((n + ps.tile - 1) / ps.tile), (unsigned)ps.threads, ps.smem, dev->stream, args, pdl));
     }
-    B200RS_CUDA(cudaEventSynchronize(dev->ev_msd));
-    if (dev->pinned_word[MSD_CTL_INELIGIBLE]) return MSD_NOT_ELIGIBLE;
-    const MsdBucketShape* fs = msd_bucket_shape(dev->pinned_word[MSD_CTL_MAX_BUCKET]);
+    // wait for the verdict (the plan kernels finish ~0.2 ms after the first launch; the stream is polled now and then so that a
+    // failed launch or a fault cannot leave this loop spinning)
+    for (uint32_t spins = 1; verdict[0] == NO_VERDICT; ++spins) {
+        if ((spins & 0x3fffu) == 0) {
+            const cudaError_t q = cudaStreamQuery(dev->stream);
+            if (q != cudaErrorNotReady && verdict[0] == NO_VERDICT) return q == cudaSuccess ? (int)cudaErrorUnknown : (int)q;
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (verdict[0] != 0) return MSD_NOT_ELIGIBLE;
+    const MsdBucketShape* fs = msd_bucket_shape(verdict[1]);
     if (!fs) return MSD_NOT_ELIGIBLE;  // (cannot happen: PL marks buckets above MSD_MAX_BUCKET ineligible; P1 only wrote the temp buffer)
     B200RS_TRY(b200rs_kernel_setup(dev, fs->kernel, fs->smem));
     {
@@ -1162,7 +1209,7 @@ int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, c
         const uint32_t* in2 = alt;
         const MsdTile* tiles_c = tiles;
         void* args[] = {&in2, &inout, (void*)&n32, &shift2, &cursor2, &tiles_c, &ctl_c, &pf_tiles};
-        B200RS_CUDA(cudaLaunchKernel(ps.p2, dim3((unsigned)(n / ps.tile + RADIX)), dim3(ps.threads), args, ps.smem, dev->stream));
+        B200RS_CUDA(msd_launch(ps.p2, (unsigned)(n / ps.tile + RADIX), (unsigned)ps.threads, ps.smem, dev->stream, args, pdl));
     }
     {
         b200rs_launch_scope scope(dev, "msd_bucket_keys", n, 8ull * n);
@@ -1171,7 +1218,7 @@ int sort_keys_msd(b200rs_device* dev, uint32_t* inout, uint64_t n, char* base, c
         uint32_t pf_buckets = (uint32_t)b200rs_exp_env("B200RS_MSD_PF", dev->num_sms * 6);
         uint32_t minus_one = 0xffffffffu;
         void* args[] = {&inout, &off_c, &minus_one, &pf_buckets};
-        B200RS_CUDA(cudaLaunchKernel(fs->kernel, dim3(MSD_BUCKETS), dim3(fs->threads), args, fs->smem, dev->stream));
+        B200RS_CUDA(msd_launch(fs->kernel, MSD_BUCKETS, (unsigned)fs->threads, fs->smem, dev->stream, args, pdl));
     }
     B200RS_CUDA(cudaGetLastError());
     return B200RS_OK;
