@@ -102,6 +102,9 @@ int b200rs_device_destroy(b200rs_device* dev) {
     if (dev->ev_start) cudaEventDestroy(dev->ev_start);
     if (dev->ev_aux[0]) cudaEventDestroy(dev->ev_aux[0]);
     if (dev->ev_aux[1]) cudaEventDestroy(dev->ev_aux[1]);
+    for (cudaEvent_t e : dev->ev_pipe) if (e) cudaEventDestroy(e);
+    for (cudaStream_t c : dev->copy) if (c) cudaStreamDestroy(c);
+    if (dev->pinned_plan) cudaFreeHost(dev->pinned_plan);
     if (dev->aux) cudaStreamDestroy(dev->aux);
     if (dev->copy_in) cudaStreamDestroy(dev->copy_in);
     if (dev->copy_out) cudaStreamDestroy(dev->copy_out);

@@ -42,6 +42,10 @@ struct b200rs_device {
     // second stream of the partitioned sort (histograms next to the exchange kernel), created on first use
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_aux[2] = {nullptr, nullptr};
+    // pipelined partitioned sort: copy-engine streams for the second half of the exchange, events that tie them to `stream`
+    cudaStream_t copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_pipe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* pinned_plan = nullptr;  // plan of the pipelined partitioned sort, read back once per sort
 
     bool profiling = false;
     std::vector<b200rs_profile_span> spans;

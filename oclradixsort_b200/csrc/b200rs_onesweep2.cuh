@@ -356,9 +356,10 @@ onesweep2_kernel(const ElemT* __restrict__ in, ElemT* __restrict__ out, uint64_t
         s.n_eff = n_eff;
         // The CTA that will take over this CTA's slot gets a ticket about pf_tiles higher: pull that tile into L2 now
         // (one bulk prefetch, nobody waits for it), so its counting phase sees L2 latency instead of HBM latency.
-        if (pf_tiles && in_aligned) {
+        if (pf_tiles) {  // (an input that is not 16-byte aligned -- the second half of a partitioned sort -- is prefetched from the boundary below)
             const uint64_t pf_base = ((uint64_t)t + pf_tiles) * Cfg::TILE;
-            if (pf_base + Cfg::TILE <= n_eff) bulk_prefetch_l2(in + pf_base, Cfg::TILE * (uint32_t)sizeof(ElemT));
+            if (pf_base + Cfg::TILE <= n_eff)
+                bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(in + pf_base) & ~(uintptr_t)15), Cfg::TILE * (uint32_t)sizeof(ElemT));
         }
         if (LOAD == LOAD_BULK) {
             const uint32_t mbar = smem_addr(&s.mbar);

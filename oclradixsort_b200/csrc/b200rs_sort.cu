@@ -1503,10 +1503,34 @@ namespace {
 //     shared -> global) per part -- the destination may be another GPU's memory (CUDA IPC mapping, NVLink): the copy engine
 //     streams it while the CTA's threads are already gone -- plus at most one 8-byte element at each ragged end.
 // Same stability argument as the scatter passes: warp-striped load order, per-warp counts, ticket-ordered tiles.
-constexpr int XP_THREADS = 256, XP_IPT = 16, XP_WARPS = XP_THREADS / 32, XP_TILE = XP_THREADS * XP_IPT, XP_MAX_PARTS = 32;
+// Shape: 7 worker warps x 32 lanes x 16 pairs (3584-pair tiles: 1.75 KB runs per destination at 16 parts) + 1 helper warp, 4 CTAs/SM.
+//
+// The helper warp (lane p = part p) owns everything that depends on other tiles, and does it WHILE the workers rank:
+//   1. the workers load their pairs, look the part up and count it (one shared-memory RED per pair into the warp's row:
+//      lanes with the same part are merged by the hardware) -- barrier;
+//   2. helper: totals and the warps' first slots; the tile's counts go out at once (tile table).  Two-level look-back:
+//      tiles form groups of XP_GROUP; a tile's exclusive prefix = [inclusive prefix of the previous group] + [counts of the
+//      tiles before it in its own group] (independent loads, one round trip); the group's last tile also publishes the group
+//      AGGREGATE at once; every tile walks the GROUP table backwards, XP_WINDOW groups = 32 tiles per step, adding aggregates until it
+//      meets an INCLUSIVE word, and the group's last tile publishes its group's.  Then the layout of the staged tile (it depends on the 16-byte
+//      phase of every destination).  Workers meanwhile: ranks (five ballots per pair) -- barrier;
+//   3. workers stage, barrier, one bulk copy per part.
+// History (2^28 pairs into 16 local parts, one B200; profiles/r2p_*, r2q_*, r2r_*): the first version counted inside the
+// ranking loop and let lane p of warp 0 walk a per-tile table 4 tiles per step after it: 1.62 ms -- 8.25 dependent L2 round
+// trips per tile (tiles start every 25 ns; an inclusive word appears a whole look-back later than the partial one), ~5 us
+// during which the CTA's other warps sat at the barrier: 37 % of a CTA's life, 42 % of all warp samples "barrier".  Four
+// ballots instead of five for <= 16 parts and the L2 prefetch of a later tile: 1.40 ms.  A lane-per-predecessor window (32
+// uncoalesced words per part and step, every warp polling): 3.5 ms, the polls alone saturate L2.  Two-level table walked after
+// the ranking: 1.30 ms, still 6.8 steps per tile -- the wait is for the slowest of the preceding tiles to FINISH RANKING.  Hence
+// the early counts and the helper warp: 1.19 ms (the helper's wait for the slowest of the preceding ~16 tiles to finish COUNTING plus
+// 3.8 steps of the group walk still outlast the ranking; 29 % of the warp samples are workers waiting for it).
+constexpr int XP_IPT = 16, XP_MAX_PARTS = 32, XP_GROUP = 8, XP_WINDOW = 4;  // look-back: tiles per group, group words per step
+constexpr uint32_t XP_VALID = 0x80000000u;  // tile table: bit 31 marks a published count
+template <int XP_WORKERS>
 struct XpSmem {
+    static constexpr int XP_TILE = XP_WORKERS * 32 * XP_IPT;
     alignas(128) uint2 staged[XP_TILE + 2 * XP_MAX_PARTS];  // every run may start one element late and end one early
-    uint32_t warp_base[XP_WARPS][XP_MAX_PARTS];             // warp counts, then the warp's first slot inside the part's run
+    uint32_t warp_base[XP_WORKERS][XP_MAX_PARTS];           // warp counts, then the warp's first slot inside the part's run
     uint32_t region[XP_MAX_PARTS];                          // staged slot of the part's first element
     uint32_t count[XP_MAX_PARTS];
     unsigned long long dst[XP_MAX_PARTS];                   // byte address of the part's run in its destination
@@ -1516,24 +1540,112 @@ struct XpSmem {
     unsigned long long n_eff;
 };
 
+// The helper warp's work (lane p = part p).  Inlined, groups of 8 tiles and 4 group words per step are what fits next to the
+// workers' XP_IPT pairs per thread without spills: 1.19 ms at 2^28 pairs into 16 local parts; groups of 16 with 8 words per
+// step 1.47 ms (64 B of spills in the workers' path), 8 words per step as a __noinline__ function 1.61 ms (the call spills).
+template <int XP_WORKERS>
+__device__ __forceinline__ void exchange_helper(XpSmem<XP_WORKERS>& s, int lane, int parts, uint32_t tile, uint32_t* lb_tile, uint64_t* lb_group,
+                                             const unsigned long long* __restrict__ part_base) {
+    uint32_t total = 0;
+    if (lane < parts) {
+#pragma unroll
+        for (int w = 0; w < XP_WORKERS; ++w) {
+            const uint32_t c = s.warp_base[w][lane];
+            s.warp_base[w][lane] = total;
+            total += c;
+        }
+    }
+    unsigned long long exclusive = 0;
+    if (lane < parts) {
+        const uint32_t q = tile % XP_GROUP, g = tile / XP_GROUP;
+        uint32_t* row = lb_tile + (uint64_t)tile * XP_MAX_PARTS + lane;
+        uint64_t* grow = lb_group + (uint64_t)g * XP_MAX_PARTS + lane;
+        st_relaxed_u32(row, XP_VALID | total);
+        // chain: the first window goes out before the group mates are collected (both round trips overlap)
+        int32_t ahead = (int32_t)g;  // groups before mine
+        const uint64_t* p = grow - XP_MAX_PARTS;
+        uint64_t w[XP_WINDOW];
+#pragma unroll
+        for (int j = 0; j < XP_WINDOW; ++j) w[j] = j < ahead ? ld_relaxed_u64(p - j * XP_MAX_PARTS) : (2ull << LB_TAG_SHIFT);  // below group 0: inclusive 0
+        // counts of the tiles before this one in its group
+        uint32_t mates = 0, got = 0;  // bit i of got: the count of the tile i + 1 places back has been added
+        const uint32_t all = (1u << q) - 1u;
+        while (got != all) {
+            uint32_t x[XP_GROUP - 1];
+#pragma unroll
+            for (int i = 0; i < XP_GROUP - 1; ++i)
+                x[i] = ((all & ~got) >> i) & 1u ? ld_relaxed_u32(row - (i + 1) * XP_MAX_PARTS) : 0u;
+#pragma unroll
+            for (int i = 0; i < XP_GROUP - 1; ++i)
+                if (x[i] & XP_VALID) { mates += x[i] & ~XP_VALID; got |= 1u << i; }
+        }
+        if (q == XP_GROUP - 1) st_relaxed_u64(grow, (1ull << LB_TAG_SHIFT) | (uint64_t)(mates + total));
+        bool done = false;
+        for (;;) {
+            int consumed = 0;
+#pragma unroll
+            for (int j = 0; j < XP_WINDOW; ++j) {
+                const uint32_t tag = (uint32_t)(w[j] >> LB_TAG_SHIFT);
+                if (!done && consumed == j && tag != 0) {
+                    exclusive += w[j] & LB_VALUE_MASK;
+                    consumed = j + 1;
+                    done = tag == 2;
+                }
+            }
+            if (done) break;
+            p -= consumed * XP_MAX_PARTS;
+            ahead -= consumed;
+#pragma unroll
+            for (int j = 0; j < XP_WINDOW; ++j) w[j] = j < ahead ? ld_relaxed_u64(p - j * XP_MAX_PARTS) : (2ull << LB_TAG_SHIFT);
+        }
+        exclusive += mates;
+        if (q == XP_GROUP - 1) st_relaxed_u64(grow, (2ull << LB_TAG_SHIFT) | (exclusive + total));
+    }
+    const unsigned long long dst = lane < parts ? part_base[lane] + 8ull * exclusive : 0ull;
+    const uint32_t phase = (uint32_t)(dst >> 3) & 1u;            // the run starts in the upper half of a 16-byte chunk
+    const uint32_t padded = (phase + total + 1u) & ~1u;           // slots the run occupies, a whole number of chunks
+    uint32_t inc = padded;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += y;
+    }
+    s.region[lane] = inc - padded + phase;
+    s.count[lane] = total;
+    s.dst[lane] = dst;
+}
+
 // SPLIT: the part of a pair is the number of thresholds (parts - 1 ascending 64-bit values, `splitters`) its key reaches,
 // instead of a table lookup on one digit: destinations then own arbitrary key ranges (exact quantiles, dist.py's splitter plan).
-template <bool BULK, bool SPLIT>
-__global__ void __launch_bounds__(XP_THREADS, 4)
+template <int XP_WORKERS, int PART_BITS /* 4: at most 16 parts, 5: at most 32 */, bool BULK, bool SPLIT>
+__global__ void __launch_bounds__((XP_WORKERS + 1) * 32, 1024 / ((XP_WORKERS + 1) * 32))
 exchange_partition_kernel(const uint2* __restrict__ in, uint64_t n, int shift, uint32_t digit_mask, const uint8_t* __restrict__ digit_lut,
                           const unsigned long long* __restrict__ splitters,
                           const unsigned long long* __restrict__ part_base /*[parts] byte addresses, 8-byte aligned*/, int parts,
-                          uint64_t* lookback /*[tiles][XP_MAX_PARTS] tagged words, zeroed*/, uint32_t* ticket,
-                          const unsigned long long* __restrict__ n_dev, uint32_t minus_one) {
+                          uint32_t* lb_tile /*[tiles][XP_MAX_PARTS] counts, zeroed*/, uint64_t* lb_group /*[tiles / XP_GROUP][XP_MAX_PARTS] tagged words, zeroed*/, uint32_t* ticket,
+                          const unsigned long long* __restrict__ n_dev, uint32_t pf_tiles /* L2 prefetch distance in tiles, 0 = off */) {
+    constexpr int XP_THREADS = (XP_WORKERS + 1) * 32, XP_TILE = XP_WORKERS * 32 * XP_IPT;
     extern __shared__ __align__(128) unsigned char xp_smem_raw[];
-    XpSmem& s = *reinterpret_cast<XpSmem*>(xp_smem_raw);
+    XpSmem<XP_WORKERS>& s = *reinterpret_cast<XpSmem<XP_WORKERS>*>(xp_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool worker = warp < XP_WORKERS;
     if (tid == 0) {
-        s.tile = atomicAdd(ticket, 1u);
-        s.n_eff = n_dev ? min((unsigned long long)n, *n_dev) : (unsigned long long)n;
+        const uint32_t t = atomicAdd(ticket, 1u);
+        const unsigned long long n_eff = n_dev ? min((unsigned long long)n, *n_dev) : (unsigned long long)n;
+        s.tile = t;
+        s.n_eff = n_eff;
+        // the CTA that takes over this CTA's slot gets a ticket about pf_tiles higher: pull that tile into L2 now
+        // (the prefetch starts at the 16-byte boundary below the tile and covers all of it but its last pair at most)
+        if (pf_tiles) {
+            const uint64_t pf_base = ((uint64_t)t + pf_tiles) * XP_TILE;
+            if (pf_base + XP_TILE <= n_eff)
+                bulk_prefetch_l2(reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(in + pf_base) & ~(uintptr_t)15), XP_TILE * (uint32_t)sizeof(uint2));
+        }
     }
-    if (!SPLIT && tid < RADIX) s.lut[tid] = digit_lut[tid];
+    if (!SPLIT)
+        for (int i = tid; i < RADIX; i += XP_THREADS) s.lut[i] = digit_lut[i];
     if (SPLIT && tid < XP_MAX_PARTS) s.splitter[tid] = tid < parts - 1 ? splitters[tid] : ~0ull;
+    for (int i = tid; i < XP_WORKERS * XP_MAX_PARTS; i += XP_THREADS) (&s.warp_base[0][0])[i] = 0;
     __syncthreads();
     n = s.n_eff;
     const uint32_t tile = s.tile;
@@ -1542,110 +1654,72 @@ exchange_partition_kernel(const uint2* __restrict__ in, uint64_t n, int shift, u
     const uint32_t valid = (uint32_t)min((uint64_t)XP_TILE, n - tile_base);
     const uint32_t slice = warp * (32 * XP_IPT) + lane;
 
+    // ---- workers: load, part, early count ----
     uint2 elem[XP_IPT];
-    const uint2* __restrict__ src = in + tile_base + slice;
-#pragma unroll
-    for (int i = 0; i < XP_IPT; ++i)
-        if (slice + i * 32 < valid) elem[i] = __ldg(src + i * 32);
-
-    // ---- ranking in registers ----
-    const uint32_t lt = lanemask_lt();
-    uint32_t xk[5];  // lane p's selector: all-ones where bit k of p is CLEAR (its match mask takes the complement of that ballot)
-#pragma unroll
-    for (int k = 0; k < 5; ++k) xk[k] = ((lane >> k) & 1) ? 0u : 0xffffffffu;
-    uint32_t cnt = 0;                  // lane p: pairs of part p seen so far by this warp
-    uint32_t rec[XP_IPT / 2];          // per item: part | rank << 5, two per register
+    uint32_t rec[XP_IPT / 2];  // per item: part | rank << 5, two per register
 #pragma unroll
     for (int i = 0; i < XP_IPT / 2; ++i) rec[i] = 0;
+    if (worker) {
+        const uint2* __restrict__ src = in + tile_base + slice;
 #pragma unroll
-    for (int i = 0; i < XP_IPT; ++i) {
-        const bool live = slice + i * 32 < valid;
-        uint32_t part = 0;
-        if (SPLIT) {
-            if (live)
-                for (int j = 0; j < parts - 1; ++j) part += (unsigned long long)elem[i].x >= s.splitter[j] ? 1u : 0u;
-        } else {
-            part = live ? (uint32_t)s.lut[(elem[i].x >> shift) & digit_mask] : 0u;
-        }
-        const uint32_t live_lanes = __ballot_sync(0xffffffffu, live);
-        uint32_t peers = live_lanes, owner = live_lanes;
+        for (int i = 0; i < XP_IPT; ++i)
+            if (slice + i * 32 < valid) elem[i] = __ldg(src + i * 32);
+        const uint32_t row = smem_addr(&s.warp_base[warp][0]);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const uint32_t b = __ballot_sync(0xffffffffu, (part >> k) & 1u);
-            peers &= ((part >> k) & 1u) ? b : ~b;   // lanes whose bit k equals mine
-            owner &= b ^ xk[k];                      // lanes whose bit k equals bit k of MY LANE NUMBER
+        for (int i = 0; i < XP_IPT; ++i) {
+            if (slice + i * 32 < valid) {
+                uint32_t part = 0;
+                if (SPLIT) {
+                    for (int j = 0; j < parts - 1; ++j) part += (unsigned long long)elem[i].x >= s.splitter[j] ? 1u : 0u;
+                } else {
+                    part = (uint32_t)s.lut[(elem[i].x >> shift) & digit_mask];
+                }
+                red_add_shared(row + 4u * part, 1u);
+                rec[i >> 1] |= part << (16 * (i & 1));
+            }
         }
-        const uint32_t base = __shfl_sync(0xffffffffu, cnt, (int)part);  // count of my part before this item
-        cnt += (uint32_t)__popc(owner);
-        const uint32_t r = base + (uint32_t)__popc(peers & lt);
-        rec[i >> 1] |= (part | (r << 5)) << (16 * (i & 1));
     }
-    s.warp_base[warp][lane] = cnt;
     __syncthreads();
 
-    // ---- warp 0, lane p = part p: totals, look-back, layout of the staged tile ----
-    if (warp == 0) {
-        uint32_t total = 0;
-        if (lane < parts) {
+    if (!worker) {
+        exchange_helper<XP_WORKERS>(s, lane, parts, tile, lb_tile, lb_group, part_base);
+    } else {
+        // ---- workers: ranking in registers ----
+        const uint32_t lt = lanemask_lt();
+        uint32_t xk[PART_BITS];  // lane p's selector: all-ones where bit k of p is CLEAR (its match mask takes the complement of that ballot)
 #pragma unroll
-            for (int w = 0; w < XP_WARPS; ++w) {
-                const uint32_t c = s.warp_base[w][lane];
-                s.warp_base[w][lane] = total;
-                total += c;
+        for (int k = 0; k < PART_BITS; ++k) xk[k] = ((lane >> k) & 1) ? 0u : 0xffffffffu;
+        uint32_t cnt = 0;  // lane p: pairs of part p seen so far by this warp
+#pragma unroll
+        for (int i = 0; i < XP_IPT; ++i) {
+            const bool live = slice + i * 32 < valid;
+            const uint32_t part = (rec[i >> 1] >> (16 * (i & 1))) & 31u;
+            const uint32_t live_lanes = __ballot_sync(0xffffffffu, live);
+            uint32_t peers = live_lanes, owner = live_lanes;
+#pragma unroll
+            for (int k = 0; k < PART_BITS; ++k) {
+                const uint32_t b = __ballot_sync(0xffffffffu, (part >> k) & 1u);
+                peers &= ((part >> k) & 1u) ? b : ~b;   // lanes whose bit k equals mine
+                owner &= b ^ xk[k];                      // lanes whose bit k equals bit k of MY LANE NUMBER
             }
+            const uint32_t base = __shfl_sync(0xffffffffu, cnt, (int)part);  // count of my part before this item
+            cnt += (uint32_t)__popc(owner);
+            const uint32_t r = base + (uint32_t)__popc(peers & lt);
+            rec[i >> 1] |= (r << 5) << (16 * (i & 1));
         }
-        uint64_t exclusive = 0;
-        if (lane < parts) {
-            const uint64_t TAG_PARTIAL = 1ull << LB_TAG_SHIFT, TAG_INCLUSIVE = 2ull << LB_TAG_SHIFT;
-            uint64_t* mine = lookback + (uint64_t)tile * XP_MAX_PARTS + lane;
-            if (tile != 0) {
-                st_relaxed_u64(mine, TAG_PARTIAL | total);
-                const uint64_t* p = mine - XP_MAX_PARTS;  // tile 0 always publishes INCLUSIVE: the walk ends there
-                int32_t ahead = (int32_t)tile;
-                bool done = false;
-                while (!done) {
-                    uint64_t w[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) w[j] = j < ahead ? ld_relaxed_u64(p - j * XP_MAX_PARTS) : 0ull;
-                    int consumed = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t tag = (uint32_t)(w[j] >> LB_TAG_SHIFT);
-                        if (!done && consumed == j && tag != 0) {
-                            exclusive += w[j] & LB_VALUE_MASK;
-                            consumed = j + 1;
-                            done = tag == 2;
-                        }
-                    }
-                    p -= consumed * XP_MAX_PARTS;
-                    ahead -= consumed;
-                }
-            }
-            st_relaxed_u64(mine, TAG_INCLUSIVE | (exclusive + total));
-        }
-        const unsigned long long dst = lane < parts ? part_base[lane] + 8ull * exclusive : 0ull;
-        const uint32_t phase = (uint32_t)(dst >> 3) & 1u;            // the run starts in the upper half of a 16-byte chunk
-        const uint32_t padded = (phase + total + 1u) & ~1u;           // slots the run occupies, a whole number of chunks
-        uint32_t inc = padded;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += y;
-        }
-        s.region[lane] = inc - padded + phase;
-        s.count[lane] = total;
-        s.dst[lane] = dst;
     }
     __syncthreads();
 
     // ---- every pair to its staged slot ----
     const uint32_t staged = smem_addr(&s.staged[0]);
+    if (worker) {
 #pragma unroll
-    for (int i = 0; i < XP_IPT; ++i) {
-        if (slice + i * 32 < valid) {
-            const uint32_t pr = (rec[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-            const uint32_t part = pr & 31u, r = pr >> 5;
-            st_shared(staged + 8u * (s.region[part] + s.warp_base[warp][part] + r), elem[i]);
+        for (int i = 0; i < XP_IPT; ++i) {
+            if (slice + i * 32 < valid) {
+                const uint32_t pr = (rec[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+                const uint32_t part = pr & 31u, r = pr >> 5;
+                st_shared(staged + 8u * (s.region[part] + s.warp_base[warp][part] + r), elem[i]);
+            }
         }
     }
     if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the staged tile is read by the async proxy below
@@ -1653,7 +1727,7 @@ exchange_partition_kernel(const uint2* __restrict__ in, uint64_t n, int shift, u
 
     // ---- write-out ----
     if (BULK) {
-        if (warp == 0 && lane < parts) {
+        if (!worker && lane < parts) {
             uint32_t a = s.region[lane], c = s.count[lane];
             unsigned long long g = s.dst[lane];
             if (c && (a & 1u)) {  // ragged head: one element up to the 16-byte boundary
@@ -1673,7 +1747,6 @@ exchange_partition_kernel(const uint2* __restrict__ in, uint64_t n, int shift, u
             for (uint32_t j = tid; j < c; j += XP_THREADS) g[j] = s.staged[a + j];
         }
     }
-    (void)minus_one;
 }
 
 // ---- histograms of the local sort, taken on the SENDING side while the exchange runs ---------------------------------
@@ -1813,15 +1886,136 @@ dist_plan_kernel(const unsigned long long* __restrict__ hist_all, int P, int me,
     (void)n_in_valid;
 }
 
+// ---- plan of the PIPELINED exchange (two halves per destination) --------------------------------------------------------
+// Same digit ranges per destination as dist_plan_kernel; every destination's range is cut once more at the digit boundary
+// closest to half of ITS pairs: half A = the lower digits, half B = the rest.  The exchange kernel then partitions into
+// 2 x world parts: part 2d is stored straight into d's receive buffer (NVLink, as before), part 2d + 1 into a staging area
+// in THIS GPU's memory, from where copy engines move it to d while the SMs already sort half A (own pairs of half B go
+// straight to their final place).  d's receive buffer: [A: source 0, source 1, ... | B: source 0, source 1, ...] -- inside
+// each half in (source rank, position) order, so the two stable local sorts leave exactly the one stable sort.
+struct DistHalfPlan {
+    unsigned long long status;                       // 1: some rank's share exceeds its receive capacity (nothing is exchanged)
+    unsigned long long recv_total, recv_a, recv_b;   // pairs this rank receives
+    unsigned long long stage_off[XP_MAX_PARTS / 2];  // pairs: start of destination d's half-B run in this rank's staging area
+    unsigned long long stage_cnt[XP_MAX_PARTS / 2];  // pairs of half B this rank sends to d (0 for d == this rank)
+    unsigned long long dst_addr[XP_MAX_PARTS / 2];   // byte address of that run in d's receive buffer
+};
+__global__ void __launch_bounds__(RADIX)
+dist_plan_halves_kernel(const unsigned long long* __restrict__ hist_all, int P, int me, const unsigned long long* __restrict__ peer_base,
+                        unsigned long long capacity, unsigned long long stage_base /* byte address of the staging area */,
+                        uint8_t* __restrict__ lut_out /*[256] digit -> part (2 x destination + half)*/, unsigned long long* __restrict__ part_base_out /*[2P]*/,
+                        unsigned long long* __restrict__ counts_out, uint32_t* __restrict__ status_out, unsigned long long n_in, DistHalfPlan* __restrict__ plan_out) {
+    __shared__ unsigned long long s_cum[RADIX + 1];
+    __shared__ unsigned long long s_scan[RADIX / 32];
+    __shared__ int s_edge[XP_MAX_PARTS / 2 + 1];
+    __shared__ int s_mid[XP_MAX_PARTS / 2];
+    __shared__ unsigned long long s_best[RADIX / 32];
+    __shared__ int s_best_b[RADIX / 32];
+    __shared__ unsigned long long s_all[XP_MAX_PARTS], s_before[XP_MAX_PARTS], s_mine[XP_MAX_PARTS];
+    const int b = threadIdx.x, lane = b & 31, warp = b >> 5;
+    unsigned long long total = 0;
+    for (int s = 0; s < P; ++s) total += hist_all[(size_t)s * RADIX + b];
+    const unsigned long long excl = block_exclusive_scan_256<unsigned long long>(total, s_scan, b);
+    s_cum[b] = excl;
+    if (b == RADIX - 1) s_cum[RADIX] = excl + total;
+    if (b == 0) { s_edge[0] = 0; s_edge[P] = RADIX; }
+    __syncthreads();
+    const unsigned long long N = s_cum[RADIX];
+    for (int r = 1; r < P; ++r) {  // (the rule of dist_plan_kernel: boundary whose cumulative count is closest to r N / P, ties to the lower digit)
+        auto dist_to = [&](int edge) {
+            const unsigned long long a = s_cum[edge] * (unsigned long long)P, t = (unsigned long long)r * N;
+            return a > t ? a - t : t - a;
+        };
+        unsigned long long best = dist_to(b);
+        int best_b = b;
+        if (b == RADIX - 1 && dist_to(RADIX) < best) { best = dist_to(RADIX); best_b = RADIX; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ob = __shfl_down_sync(0xffffffffu, best, o);
+            const int obb = __shfl_down_sync(0xffffffffu, best_b, o);
+            if (ob < best || (ob == best && obb < best_b)) { best = ob; best_b = obb; }
+        }
+        if (lane == 0) { s_best[warp] = best; s_best_b[warp] = best_b; }
+        __syncthreads();
+        if (b == 0) {
+            for (int w = 1; w < RADIX / 32; ++w)
+                if (s_best[w] < best || (s_best[w] == best && s_best_b[w] < best_b)) { best = s_best[w]; best_b = s_best_b[w]; }
+            s_edge[r] = max(best_b, s_edge[r - 1]);
+        }
+        __syncthreads();
+    }
+    if (b < P) {  // the cut inside destination b's range
+        const int lo = s_edge[b], hi = s_edge[b + 1];
+        const unsigned long long tot = s_cum[hi] - s_cum[lo];
+        int best_k = lo;
+        unsigned long long best = tot;  // |2 * 0 - tot|
+        for (int k = lo + 1; k <= hi; ++k) {
+            const unsigned long long a2 = 2ull * (s_cum[k] - s_cum[lo]);
+            const unsigned long long dk = a2 > tot ? a2 - tot : tot - a2;
+            if (dk < best) { best = dk; best_k = k; }
+        }
+        s_mid[b] = best_k;
+    }
+    __syncthreads();
+    int owner = 0;
+    for (int r = 1; r < P; ++r) owner += (s_edge[r] <= b) ? 1 : 0;
+    lut_out[b] = (uint8_t)(2 * owner + (b >= s_mid[owner] ? 1 : 0));
+    if (b < 2 * P) {  // part b: pairs every source sends, those of lower ranks, mine
+        const int d = b >> 1;
+        const int lo = (b & 1) ? s_mid[d] : s_edge[d], hi = (b & 1) ? s_edge[d + 1] : s_mid[d];
+        unsigned long long before_me = 0, all = 0, mine = 0;
+        for (int s = 0; s < P; ++s) {
+            unsigned long long c = 0;
+            for (int k = lo; k < hi; ++k) c += hist_all[(size_t)s * RADIX + k];
+            if (s < me) before_me += c;
+            if (s == me) mine = c;
+            all += c;
+        }
+        s_all[b] = all; s_before[b] = before_me; s_mine[b] = mine;
+    }
+    __syncthreads();
+    if (b == 0) {
+        bool ok = true;
+        for (int d = 0; d < P; ++d) ok = ok && s_all[2 * d] + s_all[2 * d + 1] <= capacity;
+        unsigned long long running = 0;
+        for (int d = 0; d < P; ++d) {
+            const unsigned long long final_b = peer_base[d] + 8ull * (s_all[2 * d] + s_before[2 * d + 1]);
+            part_base_out[2 * d] = peer_base[d] + 8ull * s_before[2 * d];
+            if (d == me) {
+                part_base_out[2 * d + 1] = final_b;
+                plan_out->stage_off[d] = 0; plan_out->stage_cnt[d] = 0; plan_out->dst_addr[d] = final_b;
+            } else {
+                part_base_out[2 * d + 1] = stage_base + 8ull * running;
+                plan_out->stage_off[d] = running; plan_out->stage_cnt[d] = s_mine[2 * d + 1]; plan_out->dst_addr[d] = final_b;
+                running += (s_mine[2 * d + 1] + 15ull) & ~15ull;  // runs start on 128-byte boundaries of the staging area
+            }
+        }
+        status_out[0] = ok ? 0u : 1u;
+        counts_out[0] = ok ? n_in : 0ull;
+        counts_out[1] = ok ? s_all[2 * me] + s_all[2 * me + 1] : 0ull;
+        plan_out->status = ok ? 0ull : 1ull;
+        plan_out->recv_a = s_all[2 * me];
+        plan_out->recv_b = s_all[2 * me + 1];
+        plan_out->recv_total = s_all[2 * me] + s_all[2 * me + 1];
+    }
+}
+
 }  // namespace
 
 namespace {
 int exchange_impl(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, int bits, const uint8_t* digit_to_part, const uint64_t* splitters,
                   const uint64_t* part_base_addr, int parts, const uint64_t* n_dev, void* temp, size_t* temp_bytes) {
     if (!dev || !temp_bytes || parts < 1 || parts > XP_MAX_PARTS) return B200RS_ERR_INVALID_ARGUMENT;
-    const uint64_t tiles = (n + XP_TILE - 1) / XP_TILE;
-    if (tiles > 0x7fffffffull) return B200RS_ERR_TOO_LARGE;
-    const size_t need = 256 + b200rs_align_up((size_t)tiles * XP_MAX_PARTS * sizeof(uint64_t), 256);
+    int workers = 7;
+#ifdef B200RS_EXPERIMENTS
+    workers = b200rs_exp_env("B200RS_XP_THREADS", 256) == 128 ? 3 : 7;
+#endif
+    const int threads = (workers + 1) * 32;
+    // (the size query must not depend on the shape: the tables are sized for the smaller tile)
+    const uint64_t tile = (uint64_t)workers * 32 * XP_IPT, tiles = (n + tile - 1) / tile, tiles_max = (n + 3 * 32 * XP_IPT - 1) / (3 * 32 * XP_IPT);
+    if (tiles_max > 0x7fffffffull) return B200RS_ERR_TOO_LARGE;
+    const size_t tile_table = b200rs_align_up((size_t)tiles_max * XP_MAX_PARTS * sizeof(uint32_t), 256);
+    const size_t need = 256 + tile_table + b200rs_align_up((size_t)(tiles_max / XP_GROUP + 1) * XP_MAX_PARTS * sizeof(uint64_t), 256);
     if (!temp) {
         *temp_bytes = need;
         return B200RS_OK;
@@ -1830,20 +2024,36 @@ int exchange_impl(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shi
     if (n == 0) return B200RS_OK;
     if (!in || (!digit_to_part && !splitters) || !part_base_addr || ((uintptr_t)temp & 255u) || ((uintptr_t)in & 7u)) return B200RS_ERR_INVALID_ARGUMENT;
     b200rs_device_guard guard(dev);
-    B200RS_CUDA(cudaMemsetAsync(temp, 0, need, dev->stream));
+    B200RS_CUDA(cudaMemsetAsync(temp, 0, 256 + (size_t)tiles * XP_MAX_PARTS * sizeof(uint32_t), dev->stream));
+    B200RS_CUDA(cudaMemsetAsync(static_cast<char*>(temp) + 256 + tile_table, 0, (size_t)(tiles / XP_GROUP + 1) * XP_MAX_PARTS * sizeof(uint64_t), dev->stream));
     const bool bulk = !b200rs_exp_env("B200RS_XP_NO_BULK", 0);
-    auto kernel = splitters ? (bulk ? exchange_partition_kernel<true, true> : exchange_partition_kernel<false, true>)
-                            : (bulk ? exchange_partition_kernel<true, false> : exchange_partition_kernel<false, false>);
-    const size_t smem = sizeof(XpSmem);
-    B200RS_TRY(b200rs_kernel_setup(dev, (const void*)kernel, smem));
+    const bool split = splitters != nullptr, wide = parts > 16;
+    const void* kernel = nullptr;
+#define B200RS_XP_PICK(T) \
+    kernel = split ? (wide ? (bulk ? (const void*)exchange_partition_kernel<T, 5, true, true> : (const void*)exchange_partition_kernel<T, 5, false, true>)   \
+                           : (bulk ? (const void*)exchange_partition_kernel<T, 4, true, true> : (const void*)exchange_partition_kernel<T, 4, false, true>))  \
+                   : (wide ? (bulk ? (const void*)exchange_partition_kernel<T, 5, true, false> : (const void*)exchange_partition_kernel<T, 5, false, false>) \
+                           : (bulk ? (const void*)exchange_partition_kernel<T, 4, true, false> : (const void*)exchange_partition_kernel<T, 4, false, false>))
+    size_t smem = 0;
+#ifdef B200RS_EXPERIMENTS
+    if (workers == 3) { B200RS_XP_PICK(3); smem = sizeof(XpSmem<3>); }
+#endif
+    if (!kernel) { B200RS_XP_PICK(7); smem = sizeof(XpSmem<7>); }
+#undef B200RS_XP_PICK
+    B200RS_TRY(b200rs_kernel_setup(dev, kernel, smem));
     uint32_t* ticket = reinterpret_cast<uint32_t*>(temp);
-    uint64_t* lookback = reinterpret_cast<uint64_t*>(static_cast<char*>(temp) + 256);
+    uint32_t* lb_tile = reinterpret_cast<uint32_t*>(static_cast<char*>(temp) + 256);
+    uint64_t* lb_group = reinterpret_cast<uint64_t*>(static_cast<char*>(temp) + 256 + tile_table);
     {
         b200rs_launch_scope scope(dev, splitters ? "exchange_pairs_splitters" : "exchange_pairs", n, 2ull * n * sizeof(uint2));
-        kernel<<<(unsigned)tiles, XP_THREADS, smem, dev->stream>>>(reinterpret_cast<const uint2*>(in), n, shift, (1u << bits) - 1u, digit_to_part,
-                                                                  reinterpret_cast<const unsigned long long*>(splitters),
-                                                                  reinterpret_cast<const unsigned long long*>(part_base_addr), parts, lookback, ticket,
-                                                                  reinterpret_cast<const unsigned long long*>(n_dev), 0xffffffffu);
+        const uint2* in2 = reinterpret_cast<const uint2*>(in);
+        uint64_t n64 = n;
+        uint32_t mask = (1u << bits) - 1u;
+        // L2 prefetch distance: tickets are handed out at ~40-80 per microsecond, a tile about 1.5 us ahead
+        uint32_t pf_tiles = (uint32_t)b200rs_exp_env("B200RS_XP_PF", 64);
+        void* args[] = {(void*)&in2, (void*)&n64, (void*)&shift, (void*)&mask, (void*)&digit_to_part, (void*)&splitters, (void*)&part_base_addr, (void*)&parts,
+                        (void*)&lb_tile, (void*)&lb_group, (void*)&ticket, (void*)&n_dev, (void*)&pf_tiles};
+        B200RS_CUDA(cudaLaunchKernel(kernel, dim3((unsigned)tiles), dim3((unsigned)threads), args, smem, dev->stream));
     }
     B200RS_CUDA(cudaGetLastError());
     return B200RS_OK;
@@ -1934,11 +2144,141 @@ int sort_pairs_devn_with_histogram(b200rs_device* dev, b200rs_pair* inout, uint6
 }
 }  // namespace
 
+namespace {
+// The pipelined form of the partitioned sort (from DIST_PIPELINE_MIN_CAPACITY pairs of receive capacity and up to 16 ranks):
+//   top-digit histogram -> allgather -> plan with two halves per destination (dist_plan_halves_kernel), read back by the host
+//   (the one host round trip of this path: the sizes of the two local sorts and of the copies) -> ONE exchange kernel: half A of
+//   every destination over NVLink, half B into the local staging area -> [copy engines: half B to the peers] || [barrier,
+//   local sort of half A on a second stream] -> barrier -> local sort of half B -> join.
+// The SMs sort while the copy engines keep NVLink busy; the unpipelined form leaves the SMs idle for the whole exchange.
+constexpr uint64_t DIST_PIPELINE_MIN_CAPACITY = 1ull << 22;
+constexpr uint64_t DIST_PIPELINE_SORT_EXTRA = 1ull << 21;  // the second sort's fixed temp overhead is covered by a plan for this many pairs
+constexpr int DIST_PIPELINE_MAX_WORLD = XP_MAX_PARTS / 2;
+
+int dist_sort_pipelined(b200rs_device* dev, const b200rs_dist_comm* comm, const uint64_t* recv_base, uint64_t recv_capacity_pairs, const b200rs_pair* in, uint64_t n,
+                        uint64_t* counts_dev, uint32_t* status_dev, void* temp, size_t* temp_bytes) {
+    const int world = comm->world, rank = comm->rank;
+    size_t xp_bytes = 0, sort_bytes = 0, extra_bytes = 0;
+    B200RS_TRY(b200rs_exchange_pairs(dev, nullptr, n, 24, 8, nullptr, nullptr, 2 * world, nullptr, nullptr, &xp_bytes));
+    B200RS_TRY(b200rs_sort_pairs_u32(dev, nullptr, recv_capacity_pairs, 32, nullptr, &sort_bytes));
+    B200RS_TRY(b200rs_sort_pairs_u32(dev, nullptr, DIST_PIPELINE_SORT_EXTRA, 32, nullptr, &extra_bytes));
+    const size_t sort_reserved = b200rs_align_up(sort_bytes, 256) + b200rs_align_up(extra_bytes, 256) + 512;
+    const size_t stage_bytes = b200rs_align_up((size_t)(n + 16ull * world) * sizeof(b200rs_pair), 256);
+    // temp: [own top histogram][gathered world x 256][peer bases 256][part bases 256][lut 256 B][plan][exchange temp][staging][sort temp A | sort temp B]
+    const size_t hist_off = 0, gathered_off = hist_off + RADIX * 8, peers_off = gathered_off + (size_t)world * RADIX * 8, parts_off = peers_off + RADIX * 8,
+                 lut_off = parts_off + RADIX * 8, plan_off = lut_off + 256, xp_off = plan_off + b200rs_align_up(sizeof(DistHalfPlan), 256),
+                 stage_off = xp_off + b200rs_align_up(xp_bytes, 256), sort_off = stage_off + stage_bytes, need = sort_off + sort_reserved;
+    if (!temp) {
+        *temp_bytes = need;
+        return B200RS_OK;
+    }
+    if (*temp_bytes < need) return B200RS_ERR_TEMP_TOO_SMALL;
+    if (!recv_base || !counts_dev || !status_dev || (n && !in) || !comm->allgather || !comm->barrier || ((uintptr_t)temp & 255u)) return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    char* base = static_cast<char*>(temp);
+    uint64_t* hist = reinterpret_cast<uint64_t*>(base + hist_off);
+    uint64_t* gathered = reinterpret_cast<uint64_t*>(base + gathered_off);
+    uint64_t* peers = reinterpret_cast<uint64_t*>(base + peers_off);
+    uint64_t* part_base = reinterpret_cast<uint64_t*>(base + parts_off);
+    uint8_t* lut = reinterpret_cast<uint8_t*>(base + lut_off);
+    DistHalfPlan* plan_dev = reinterpret_cast<DistHalfPlan*>(base + plan_off);
+    char* stage = base + stage_off;
+    if (!dev->aux) {
+        B200RS_CUDA(cudaStreamCreateWithFlags(&dev->aux, cudaStreamNonBlocking));
+        B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_aux[0], cudaEventDisableTiming));
+        B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_aux[1], cudaEventDisableTiming));
+    }
+    if (!dev->copy[0]) {
+        for (int i = 0; i < 2; ++i) B200RS_CUDA(cudaStreamCreateWithFlags(&dev->copy[i], cudaStreamNonBlocking));
+        for (cudaEvent_t& e : dev->ev_pipe) B200RS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        B200RS_CUDA(cudaHostAlloc(&dev->pinned_plan, sizeof(DistHalfPlan), cudaHostAllocDefault));
+    }
+    cudaEvent_t ev_exchanged = dev->ev_pipe[0], ev_copied0 = dev->ev_pipe[1], ev_copied1 = dev->ev_pipe[2], ev_a_landed = dev->ev_pipe[3], ev_a_sorted = dev->ev_pipe[4];
+
+    B200RS_CUDA(cudaMemcpyAsync(peers, recv_base, (size_t)world * 8, cudaMemcpyHostToDevice, dev->stream));  // (pageable source: staged by the runtime before the call returns)
+    B200RS_TRY(b200rs_digit_histogram_pairs(dev, in, n, 24, 8, hist));
+    // the all-gather also orders this step after every rank's previous local sorts: nobody overwrites a receive buffer that is still being read
+    {
+        const int rc = comm->allgather(comm->user, hist, gathered, RADIX * 8);
+        if (rc != 0) return rc;
+    }
+    {
+        b200rs_launch_scope scope(dev, "dist_plan_halves", (uint64_t)world * RADIX, (uint64_t)world * RADIX * 8);
+        dist_plan_halves_kernel<<<1, RADIX, 0, dev->stream>>>(reinterpret_cast<const unsigned long long*>(gathered), world, rank, reinterpret_cast<const unsigned long long*>(peers),
+                                                              recv_capacity_pairs, (unsigned long long)(uintptr_t)stage, lut, reinterpret_cast<unsigned long long*>(part_base),
+                                                              reinterpret_cast<unsigned long long*>(counts_dev), status_dev, n, plan_dev);
+    }
+    B200RS_CUDA(cudaGetLastError());
+    B200RS_CUDA(cudaMemcpyAsync(dev->pinned_plan, plan_dev, sizeof(DistHalfPlan), cudaMemcpyDeviceToHost, dev->stream));
+    B200RS_CUDA(cudaStreamSynchronize(dev->stream));
+    const DistHalfPlan plan = *static_cast<const DistHalfPlan*>(dev->pinned_plan);
+    if (plan.status != 0) return B200RS_OK;  // status_dev[0] = 1, counts_dev = 0: the caller re-plans (same contract as the unpipelined form)
+
+    size_t have = xp_bytes;
+    B200RS_TRY(b200rs_exchange_pairs(dev, in, n, 24, 8, lut, part_base, 2 * world, counts_dev, base + xp_off, &have));
+    B200RS_CUDA(cudaEventRecord(ev_exchanged, dev->stream));
+    // half B: one copy per peer, farthest-first rotation so that no destination is everybody's first target
+    B200RS_CUDA(cudaStreamWaitEvent(dev->copy[0], ev_exchanged, 0));
+    B200RS_CUDA(cudaStreamWaitEvent(dev->copy[1], ev_exchanged, 0));
+    for (int i = 1; i < world; ++i) {
+        const int d = (rank + i) % world;
+        if (plan.stage_cnt[d] == 0) continue;
+        dev->launches++;
+        B200RS_CUDA(cudaMemcpyAsync(reinterpret_cast<void*>((uintptr_t)plan.dst_addr[d]), stage + 8ull * plan.stage_off[d], 8ull * plan.stage_cnt[d], cudaMemcpyDeviceToDevice,
+                                    dev->copy[i & 1]));
+    }
+    B200RS_CUDA(cudaEventRecord(ev_copied0, dev->copy[0]));
+    B200RS_CUDA(cudaEventRecord(ev_copied1, dev->copy[1]));
+    {
+        const int rc = comm->barrier(comm->user);  // every rank's exchange kernel is done: all halves A have landed
+        if (rc != 0) return rc;
+    }
+    B200RS_CUDA(cudaEventRecord(ev_a_landed, dev->stream));
+
+    b200rs_pair* mine = reinterpret_cast<b200rs_pair*>(recv_base[rank]);
+    size_t bytes_a = 0, bytes_b = 0;
+    B200RS_TRY(b200rs_sort_pairs_u32(dev, nullptr, plan.recv_a, 32, nullptr, &bytes_a));
+    B200RS_TRY(b200rs_sort_pairs_u32(dev, nullptr, plan.recv_b, 32, nullptr, &bytes_b));
+    const size_t temp_b_off = b200rs_align_up(bytes_a, 256);
+    const bool concurrent = temp_b_off + b200rs_align_up(bytes_b, 256) <= sort_reserved && !b200rs_exp_env("B200RS_DIST_SEQUENTIAL_SORTS", 0);
+    int rc_a = B200RS_OK;
+    if (concurrent) {  // half A is sorted on the second stream while the copy engines deliver half B
+        B200RS_CUDA(cudaStreamWaitEvent(dev->aux, ev_a_landed, 0));
+        cudaStream_t main_stream = dev->stream;
+        dev->stream = dev->aux;
+        size_t h = bytes_a;
+        rc_a = b200rs_sort_pairs_u32(dev, mine, plan.recv_a, 32, base + sort_off, &h);
+        dev->stream = main_stream;
+        if (rc_a != B200RS_OK) return rc_a;
+        B200RS_CUDA(cudaEventRecord(ev_a_sorted, dev->aux));
+    }
+    B200RS_CUDA(cudaStreamWaitEvent(dev->stream, ev_copied0, 0));
+    B200RS_CUDA(cudaStreamWaitEvent(dev->stream, ev_copied1, 0));
+    {
+        const int rc = comm->barrier(comm->user);  // every rank's copies are done: all halves B have landed
+        if (rc != 0) return rc;
+    }
+    if (!concurrent) {
+        size_t h = bytes_a;
+        B200RS_TRY(b200rs_sort_pairs_u32(dev, mine, plan.recv_a, 32, base + sort_off, &h));
+    }
+    {
+        size_t h = bytes_b;
+        B200RS_TRY(b200rs_sort_pairs_u32(dev, mine + plan.recv_a, plan.recv_b, 32, base + sort_off + (concurrent ? temp_b_off : 0), &h));
+    }
+    if (concurrent) B200RS_CUDA(cudaStreamWaitEvent(dev->stream, ev_a_sorted, 0));
+    return B200RS_OK;
+}
+}  // namespace
+
 // ---- the whole partitioned sort of one rank (see include/b200rs.h) -------------------------------------------------------
 extern "C" int b200rs_dist_sort_pairs_u32(b200rs_device* dev, const b200rs_dist_comm* comm, const uint64_t* recv_base, uint64_t recv_capacity_pairs,
                                           const b200rs_pair* in, uint64_t n, uint64_t* counts_dev, uint32_t* status_dev, void* temp, size_t* temp_bytes) {
     if (!dev || !comm || !temp_bytes || comm->world < 1 || comm->world > XP_MAX_PARTS || comm->rank < 0 || comm->rank >= comm->world) return B200RS_ERR_INVALID_ARGUMENT;
     const int world = comm->world;
+    // (the choice depends only on what is the same on every rank: the ranks must run the same sequence of collectives)
+    if (world >= 2 && world <= DIST_PIPELINE_MAX_WORLD && recv_capacity_pairs >= DIST_PIPELINE_MIN_CAPACITY && !b200rs_exp_env("B200RS_DIST_NO_PIPELINE", 0))
+        return dist_sort_pipelined(dev, comm, recv_base, recv_capacity_pairs, in, n, counts_dev, status_dev, temp, temp_bytes);
     // temp: [own top histogram 256 x u64][gathered world x 256 x u64][peer bases 256 x u64][part bases 256 x u64][lut 256]
     //       [own destination tables world x 3 x 256 x u64][gathered world x that][histograms of the local sort 4 x 256 x u64][exchange temp][local sort temp]
     size_t xp_bytes = 0, sort_bytes = 0;

@@ -45,6 +45,11 @@ def main():
     # skewed inputs with the DEFAULT slack: the digit-range plan overflows and the sort re-plans with exact splitters
     skewed = [("allequal", 400_000), ("hotdigit", 300_001), ("and3", (1 << 19) + 5)]
     runs = [(c, m, float(world) + 0.5) for c in cases for m in modes] + [(c, m, 1.25) for c in skewed for m in modes[:2]]
+    # receive capacity >= 2^22 pairs: the PIPELINED form of b200rs_dist_sort_pairs_u32 (two halves per destination, the second
+    # one moved by copy engines while the first is sorted); ragged sizes, an input whose plan overflows (splitter fallback)
+    # and one whose top-digit ranges cannot be halved evenly
+    runs += [(("uniform", 3_000_001 + 4099 * rank), modes[1], 1.5), (("skewtop", 2_600_003), modes[1], float(world) + 0.5), (("and3", 3_500_001), modes[1], 1.25),
+             (("lowentropy", 4_300_000 + rank), modes[1], float(world) + 0.5)]
     for (kind, n), (exchange, layout), slack in runs:
         kv = make_input(kind, rank, n)
         src = torch.from_numpy(kv.view(np.int64).reshape(-1).copy()).cuda()

@@ -96,7 +96,7 @@ def test_partitioned_sort_two_gpus_nccl():
            "--master-port", "29533", os.path.join(ROOT, "tests", "dist_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
-    assert r.stdout.count("bit-exact=True") == 15, r.stdout[-3000:]  # 3 inputs x {nccl, p2p/dest, p2p/bins} + 3 skewed inputs x {nccl, p2p/dest}
+    assert r.stdout.count("bit-exact=True") == 19, r.stdout[-3000:]  # 3 inputs x {nccl, p2p/dest, p2p/bins} + 3 skewed inputs x {nccl, p2p/dest} + 4 pipelined
 
 
 def test_cpp_caller_of_the_partitioned_sort(tmp_path):
@@ -108,7 +108,7 @@ def test_cpp_caller_of_the_partitioned_sort(tmp_path):
     exe = os.path.join(ROOT, "tools", "_build", "dist_dropin")
     if not os.path.exists(exe):
         subprocess.run(["make", "-s", "-C", ROOT, "dist_test"], check=True)
-    for world, n in ((2, 300007), (min(torch.cuda.device_count(), 4), 1 << 20)):
+    for world, n in ((2, 300007), (min(torch.cuda.device_count(), 4), 1 << 20), (2, 3_400_007)):  # (the last one: pipelined form)
         r = subprocess.run([exe, str(world), str(n)], cwd=tmp_path, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "DIST DROPIN OK" in r.stdout, (r.stdout + r.stderr)[-2000:]
 
@@ -125,15 +125,15 @@ def _device_ops():
 
 def test_exchange_kernel_matches_numpy_stable_partition():
     """b200rs_exchange_pairs (the few-parts kernel with bulk copies) on one GPU: the parts' base addresses point into one
-    local buffer, so the result must equal numpy's stable partition; sizes around the 4096-pair tile, 1..32 parts, runs
+    local buffer, so the result must equal numpy's stable partition; sizes around the 2048-pair tile, 1..32 parts (4 and 5 part bits), runs
     that start on odd element boundaries (ragged 16-byte ends), empty parts."""
     import torch
 
     from oclradixsort_b200._lib import check, lib
     ob, d, p, ops = _device_ops()
     rng = np.random.default_rng(5)
-    for n in (1, 2, 4095, 4096, 4097, 123457, 1_000_003):
-        for parts in (1, 2, 3, 8, 32):
+    for n in (1, 2, 2047, 2048, 2049, 4095, 4096, 4097, 123457, 1_000_003):
+        for parts in (1, 2, 3, 8, 16, 17, 32):
             kv = np.empty((n, 2), dtype=np.uint32)
             kv[:, 0] = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
             kv[:, 1] = np.arange(n, dtype=np.uint32)
