@@ -199,13 +199,20 @@ int b200rs_sort_pairs_u32_devn(b200rs_device* dev, b200rs_pair* inout, uint64_t 
  *   barrier(user)                               returns (or is stream-ordered) after every rank's work enqueued so far on its
  *                                               handle's stream has completed: peer stores have landed.
  * Steps: top-digit histogram -> allgather -> on-device plan (contiguous digit ranges of about N / world pairs per rank) ->
- * b200rs_exchange_pairs straight into the ranks' receive buffers recv_base[0 .. world) (device-visible addresses of EVERY
- * rank's receive buffer, own included; peers' through b200rs_ipc_import or peer access) -> barrier -> local stable sort of
- * what arrived.  The sorted pairs of this rank are left at recv_base[rank]; counts_dev[1] (device, 2 x u64) = how many;
- * status_dev[0] = 1 when a rank's share exceeds recv_capacity_pairs (nothing is exchanged then; the caller re-plans, e.g.
- * oclradixsort_b200/dist.py's splitter path).  No host round trip inside.  Equal keys keep global input order: the
- * concatenation of the ranks' outputs is the stable sort of the concatenated input.  Temp: size query as usual
- * (recv_capacity_pairs must be the same on every rank).
+ * exchange straight into the ranks' receive buffers recv_base[0 .. world) (device-visible addresses of EVERY rank's receive
+ * buffer, own included; peers' through b200rs_ipc_import or peer access) -> barrier -> local stable sort of what arrived.
+ * The sorted pairs of this rank are left at recv_base[rank]; counts_dev[1] (device, 2 x u64) = how many; status_dev[0] = 1
+ * when a rank's share exceeds recv_capacity_pairs (nothing is exchanged then; the caller re-plans, e.g.
+ * oclradixsort_b200/dist.py's splitter path).  Equal keys keep global input order: the concatenation of the ranks' outputs
+ * is the stable sort of the concatenated input.
+ * Two forms, chosen from recv_capacity_pairs and world only (the same on every rank, so all ranks run the same collectives):
+ *   - below 2^22 pairs of capacity, or beyond 16 ranks: one exchange kernel (b200rs_exchange_pairs), one barrier, one local
+ *     sort; no host round trip inside (collectives per call: 1 or 2 allgathers, 1 barrier);
+ *   - otherwise PIPELINED: every destination's digit range is cut in two halves A | B.  One exchange kernel stores half A over
+ *     NVLink and stages half B in this GPU's memory; copy engines then move half B to the peers WHILE half A is sorted on a
+ *     second stream; half B is sorted when it has landed.  The host reads the plan back once (sizes of the copies and of the
+ *     two sorts: the call blocks until the plan kernel has run, the rest is stream-ordered as before; 1 allgather, 2 barriers).
+ * Temp: size query as usual (recv_capacity_pairs must be the same on every rank).
  */
 typedef int (*b200rs_allgather_fn)(void* user, const void* send_dev, void* recv_dev, size_t bytes);
 typedef int (*b200rs_barrier_fn)(void* user);

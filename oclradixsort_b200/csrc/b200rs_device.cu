@@ -104,6 +104,7 @@ int b200rs_device_destroy(b200rs_device* dev) {
     if (dev->ev_aux[1]) cudaEventDestroy(dev->ev_aux[1]);
     for (cudaEvent_t e : dev->ev_pipe) if (e) cudaEventDestroy(e);
     for (cudaStream_t c : dev->copy) if (c) cudaStreamDestroy(c);
+    for (cudaEvent_t e : dev->ev_copied) if (e) cudaEventDestroy(e);
     if (dev->pinned_plan) cudaFreeHost(dev->pinned_plan);
     if (dev->aux) cudaStreamDestroy(dev->aux);
     if (dev->copy_in) cudaStreamDestroy(dev->copy_in);

@@ -43,7 +43,8 @@ struct b200rs_device {
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_aux[2] = {nullptr, nullptr};
     // pipelined partitioned sort: copy-engine streams for the second half of the exchange, events that tie them to `stream`
-    cudaStream_t copy[2] = {nullptr, nullptr};
+    cudaStream_t copy[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_copied[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_pipe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void* pinned_plan = nullptr;  // plan of the pipelined partitioned sort, read back once per sort
 

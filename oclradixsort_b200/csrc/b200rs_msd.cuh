@@ -479,7 +479,7 @@ msd_partition_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out
 // shared memory.  Counter words and wp[] are stored XOR-swizzled inside each thread's scan range so the scan's 128-bit
 // accesses are conflict-free.
 //
-// Measured and rejected (profiles/r2f_msd_perf.txt): writing the sorted bucket back FROM the counters (no ranks, no lookup,
+// Measured and rejected (profiles/r2f_msd_perf_count_emit_rejected.txt): writing the sorted bucket back FROM the counters (no ranks, no lookup,
 // no staging: lane l walks word 32 r + l of row r and peels its non-empty nibbles off with ffs) -- only 39 % of the lanes
 // have a non-empty word and a row of 32 words holds 16 keys, so the walk costs 300 warp instructions per 32 keys against
 // 27 for the lookup: 2.94 ms instead of 0.88 at 2^28.

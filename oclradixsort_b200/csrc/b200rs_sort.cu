@@ -1904,7 +1904,8 @@ __global__ void __launch_bounds__(RADIX)
 dist_plan_halves_kernel(const unsigned long long* __restrict__ hist_all, int P, int me, const unsigned long long* __restrict__ peer_base,
                         unsigned long long capacity, unsigned long long stage_base /* byte address of the staging area */,
                         uint8_t* __restrict__ lut_out /*[256] digit -> part (2 x destination + half)*/, unsigned long long* __restrict__ part_base_out /*[2P]*/,
-                        unsigned long long* __restrict__ counts_out, uint32_t* __restrict__ status_out, unsigned long long n_in, DistHalfPlan* __restrict__ plan_out) {
+                        unsigned long long* __restrict__ counts_out, uint32_t* __restrict__ status_out, unsigned long long n_in, DistHalfPlan* __restrict__ plan_out,
+                        uint32_t a_permille /* share of a destination's pairs that half A should hold */) {
     __shared__ unsigned long long s_cum[RADIX + 1];
     __shared__ unsigned long long s_scan[RADIX / 32];
     __shared__ int s_edge[XP_MAX_PARTS / 2 + 1];
@@ -1948,10 +1949,11 @@ dist_plan_halves_kernel(const unsigned long long* __restrict__ hist_all, int P, 
         const int lo = s_edge[b], hi = s_edge[b + 1];
         const unsigned long long tot = s_cum[hi] - s_cum[lo];
         int best_k = lo;
-        unsigned long long best = tot;  // |2 * 0 - tot|
+        const unsigned long long want = (unsigned long long)a_permille * tot;
+        unsigned long long best = want;  // |1000 * 0 - want|
         for (int k = lo + 1; k <= hi; ++k) {
-            const unsigned long long a2 = 2ull * (s_cum[k] - s_cum[lo]);
-            const unsigned long long dk = a2 > tot ? a2 - tot : tot - a2;
+            const unsigned long long a = 1000ull * (s_cum[k] - s_cum[lo]);
+            const unsigned long long dk = a > want ? a - want : want - a;
             if (dk < best) { best = dk; best_k = k; }
         }
         s_mid[b] = best_k;
@@ -2154,6 +2156,7 @@ namespace {
 constexpr uint64_t DIST_PIPELINE_MIN_CAPACITY = 1ull << 22;
 constexpr uint64_t DIST_PIPELINE_SORT_EXTRA = 1ull << 21;  // the second sort's fixed temp overhead is covered by a plan for this many pairs
 constexpr int DIST_PIPELINE_MAX_WORLD = XP_MAX_PARTS / 2;
+constexpr int DIST_PIPELINE_A_PERMILLE = 500;  // half A's share of every destination's pairs
 
 int dist_sort_pipelined(b200rs_device* dev, const b200rs_dist_comm* comm, const uint64_t* recv_base, uint64_t recv_capacity_pairs, const b200rs_pair* in, uint64_t n,
                         uint64_t* counts_dev, uint32_t* status_dev, void* temp, size_t* temp_bytes) {
@@ -2188,12 +2191,17 @@ int dist_sort_pipelined(b200rs_device* dev, const b200rs_dist_comm* comm, const 
         B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_aux[0], cudaEventDisableTiming));
         B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_aux[1], cudaEventDisableTiming));
     }
+    constexpr int COPY_STREAMS = 8;  // one copy per peer in flight (up to 8): 2 streams moved ~450 GB/s per GPU, see profiles/r2u_*
     if (!dev->copy[0]) {
-        for (int i = 0; i < 2; ++i) B200RS_CUDA(cudaStreamCreateWithFlags(&dev->copy[i], cudaStreamNonBlocking));
+        for (int i = 0; i < COPY_STREAMS; ++i) {
+            B200RS_CUDA(cudaStreamCreateWithFlags(&dev->copy[i], cudaStreamNonBlocking));
+            B200RS_CUDA(cudaEventCreateWithFlags(&dev->ev_copied[i], cudaEventDisableTiming));
+        }
         for (cudaEvent_t& e : dev->ev_pipe) B200RS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         B200RS_CUDA(cudaHostAlloc(&dev->pinned_plan, sizeof(DistHalfPlan), cudaHostAllocDefault));
     }
-    cudaEvent_t ev_exchanged = dev->ev_pipe[0], ev_copied0 = dev->ev_pipe[1], ev_copied1 = dev->ev_pipe[2], ev_a_landed = dev->ev_pipe[3], ev_a_sorted = dev->ev_pipe[4];
+    cudaEvent_t ev_exchanged = dev->ev_pipe[0], ev_a_landed = dev->ev_pipe[3], ev_a_sorted = dev->ev_pipe[4];
+    const int copy_streams = b200rs_exp_env("B200RS_DIST_COPY_STREAMS", COPY_STREAMS) < COPY_STREAMS ? (b200rs_exp_env("B200RS_DIST_COPY_STREAMS", COPY_STREAMS) < 1 ? 1 : b200rs_exp_env("B200RS_DIST_COPY_STREAMS", COPY_STREAMS)) : COPY_STREAMS;
 
     B200RS_CUDA(cudaMemcpyAsync(peers, recv_base, (size_t)world * 8, cudaMemcpyHostToDevice, dev->stream));  // (pageable source: staged by the runtime before the call returns)
     B200RS_TRY(b200rs_digit_histogram_pairs(dev, in, n, 24, 8, hist));
@@ -2206,7 +2214,8 @@ int dist_sort_pipelined(b200rs_device* dev, const b200rs_dist_comm* comm, const 
         b200rs_launch_scope scope(dev, "dist_plan_halves", (uint64_t)world * RADIX, (uint64_t)world * RADIX * 8);
         dist_plan_halves_kernel<<<1, RADIX, 0, dev->stream>>>(reinterpret_cast<const unsigned long long*>(gathered), world, rank, reinterpret_cast<const unsigned long long*>(peers),
                                                               recv_capacity_pairs, (unsigned long long)(uintptr_t)stage, lut, reinterpret_cast<unsigned long long*>(part_base),
-                                                              reinterpret_cast<unsigned long long*>(counts_dev), status_dev, n, plan_dev);
+                                                              reinterpret_cast<unsigned long long*>(counts_dev), status_dev, n, plan_dev,
+                                                              (uint32_t)b200rs_exp_env("B200RS_DIST_A_PERMILLE", DIST_PIPELINE_A_PERMILLE));
     }
     B200RS_CUDA(cudaGetLastError());
     B200RS_CUDA(cudaMemcpyAsync(dev->pinned_plan, plan_dev, sizeof(DistHalfPlan), cudaMemcpyDeviceToHost, dev->stream));
@@ -2218,17 +2227,15 @@ int dist_sort_pipelined(b200rs_device* dev, const b200rs_dist_comm* comm, const 
     B200RS_TRY(b200rs_exchange_pairs(dev, in, n, 24, 8, lut, part_base, 2 * world, counts_dev, base + xp_off, &have));
     B200RS_CUDA(cudaEventRecord(ev_exchanged, dev->stream));
     // half B: one copy per peer, farthest-first rotation so that no destination is everybody's first target
-    B200RS_CUDA(cudaStreamWaitEvent(dev->copy[0], ev_exchanged, 0));
-    B200RS_CUDA(cudaStreamWaitEvent(dev->copy[1], ev_exchanged, 0));
+    for (int c = 0; c < copy_streams; ++c) B200RS_CUDA(cudaStreamWaitEvent(dev->copy[c], ev_exchanged, 0));
     for (int i = 1; i < world; ++i) {
         const int d = (rank + i) % world;
         if (plan.stage_cnt[d] == 0) continue;
         dev->launches++;
         B200RS_CUDA(cudaMemcpyAsync(reinterpret_cast<void*>((uintptr_t)plan.dst_addr[d]), stage + 8ull * plan.stage_off[d], 8ull * plan.stage_cnt[d], cudaMemcpyDeviceToDevice,
-                                    dev->copy[i & 1]));
+                                    dev->copy[(i - 1) % copy_streams]));
     }
-    B200RS_CUDA(cudaEventRecord(ev_copied0, dev->copy[0]));
-    B200RS_CUDA(cudaEventRecord(ev_copied1, dev->copy[1]));
+    for (int c = 0; c < copy_streams; ++c) B200RS_CUDA(cudaEventRecord(dev->ev_copied[c], dev->copy[c]));
     {
         const int rc = comm->barrier(comm->user);  // every rank's exchange kernel is done: all halves A have landed
         if (rc != 0) return rc;
@@ -2252,8 +2259,7 @@ int dist_sort_pipelined(b200rs_device* dev, const b200rs_dist_comm* comm, const 
         if (rc_a != B200RS_OK) return rc_a;
         B200RS_CUDA(cudaEventRecord(ev_a_sorted, dev->aux));
     }
-    B200RS_CUDA(cudaStreamWaitEvent(dev->stream, ev_copied0, 0));
-    B200RS_CUDA(cudaStreamWaitEvent(dev->stream, ev_copied1, 0));
+    for (int c = 0; c < copy_streams; ++c) B200RS_CUDA(cudaStreamWaitEvent(dev->stream, dev->ev_copied[c], 0));
     {
         const int rc = comm->barrier(comm->user);  // every rank's copies are done: all halves B have landed
         if (rc != 0) return rc;
