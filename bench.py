@@ -515,6 +515,14 @@ def main() -> None:
             keys_line = dict(uni, workload=f"keys_u32_uniform_2^{args.log2_pairs_per_gpu}", algorithmic_bytes_per_key=36,
                              path="MSD pipeline (joint top-16 histogram, 2 unstable 8-bit partition passes, counting sort per bucket) when every top-16 bucket is small, else 4 LSD passes",
                              target="north_star: >= 0.70 of the HBM roofline at 2^28 keys")
+            try:  # DRAM bytes of the MSD chain's kernels from the committed ncu --set full capture (the path moves 28 B/key, the roofline figure uses 36)
+                with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                    msd = json.load(f).get(f"msd_keys_2^{args.log2_pairs_per_gpu}")
+                if msd:
+                    keys_line["traffic"] = sum(v["dram_bytes"] for v in msd.values())
+                    keys_line["path_algorithmic_bytes"] = sum(v["algorithmic"] for v in msd.values())
+            except Exception:
+                pass
             ts_scan, _ = timeit(lambda x: pp.scan(dev, ob.Buffer(dev, n, np.uint32, ptr=x.data_ptr()), ob.Buffer(dev, n, np.uint32, ptr=x.data_ptr()), n), u)
             t_scan = min(ts_scan)
             extras = {

@@ -10,7 +10,7 @@ for r in rows[1:]:
     val = float(r[idx["Metric Value"]].replace(",", "")); unit = r[idx["Metric Unit"]]
     us = val / 1000.0 if unit in ("ns", "nsecond") else val if unit in ("us", "usecond") else val * 1000.0
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += us
-ours = {k: v for k, v in agg.items() if re.search(r"onesweep|digit_histogram|digit_start|scan_|copy_back|partition|dist_plan", k)}
+ours = {k: v for k, v in agg.items() if re.search(r"onesweep|digit_histogram|digit_start|scan_|copy_back|partition|dist_plan|msd_|mid_sort|small_sort|exchange_|fill_kernel|copy_u32", k)}
 tot = sum(v[1] for v in ours.values())
 print("| kernel | launches | total ms | avg us | share |\n|---|---:|---:|---:|---:|")
 for k, (c, us) in sorted(ours.items(), key=lambda kv: -kv[1][1]):
