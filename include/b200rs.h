@@ -183,6 +183,19 @@ int b200rs_filtered_histograms_pairs(b200rs_device* dev, const b200rs_pair* in, 
  */
 int b200rs_dist_plan(b200rs_device* dev, const uint64_t* hist_all, int world, int rank, const uint64_t* peer_base, uint64_t capacity,
                      uint64_t n_in, uint8_t* lut_out, uint64_t* part_base_out, uint64_t* counts_out, uint32_t* status_out);
+/*
+ * Plan of the PIPELINED partitioned sort (see b200rs_dist_sort_pairs_u32): the digit ranges of b200rs_dist_plan, every
+ * destination's range cut once more into halves A | B at the digit boundary where A holds closest to a_permille / 1000 of
+ * the destination's pairs.  lut_out[256]: digit -> part = 2 x destination + half; part_base_out[2 x world]: where THIS rank's
+ * pairs of each part go -- (d, A): inside d's receive buffer; (d, B), d != rank: inside this rank's staging area at
+ * stage_base (runs on 128-byte boundaries); (rank, B): its final place; counts_out / status_out as b200rs_dist_plan.
+ * plan_out (device, 52 x u64, what the host reads back): [0] status, [1] pairs this rank receives, [2] of them in half A,
+ * [3] in half B, [4 + d] staging offset (pairs) of destination d's half-B run, [20 + d] its length, [36 + d] the byte
+ * address it is copied to in d's receive buffer.  world <= 16.  Host mirror: plan_exchange_halves() in oclradixsort_b200/dist.py.
+ */
+int b200rs_dist_plan_halves(b200rs_device* dev, const uint64_t* hist_all, int world, int rank, const uint64_t* peer_base, uint64_t capacity,
+                            uint64_t stage_base, uint64_t n_in, int a_permille, uint8_t* lut_out, uint64_t* part_base_out, uint64_t* counts_out,
+                            uint32_t* status_out, uint64_t* plan_out);
 /* b200rs_sort_pairs_u32 whose element count min(n_max, *n_dev) is read on the device (temp is sized for n_max).  Only the
  * first *n_dev elements are sorted; with an ODD number of passes (sort_bits <= 8 or in 17..24) the final copy back covers
  * n_max elements, so inout[*n_dev .. n_max) then holds unspecified values. */

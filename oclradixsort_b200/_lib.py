@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200rs_exchange_pairs_by_splitters": (_int, [c_dev, _vp, _u64, _vp, _vp, _int, _vp, _P(_sz)]),
     "b200rs_filtered_histograms_pairs": (_int, [c_dev, _vp, _u64, _int, _vp, _int, _vp]),
     "b200rs_dist_plan": (_int, [c_dev, _vp, _int, _int, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
+    "b200rs_dist_plan_halves": (_int, [c_dev, _vp, _int, _int, _vp, _u64, _u64, _u64, _int, _vp, _vp, _vp, _vp, _vp]),
     "b200rs_sort_pairs_u32_devn": (_int, [c_dev, _vp, _u64, _vp, _int, _vp, _P(_sz)]),
     "b200rs_enable_peer_access": (_int, [c_dev, _int]),
     "b200rs_ipc_export": (_int, [c_dev, _vp, ctypes.c_char_p]),

@@ -2138,6 +2138,25 @@ extern "C" int b200rs_dist_plan(b200rs_device* dev, const uint64_t* hist_all, in
     return B200RS_OK;
 }
 
+extern "C" int b200rs_dist_plan_halves(b200rs_device* dev, const uint64_t* hist_all, int world, int rank, const uint64_t* peer_base, uint64_t capacity,
+                                       uint64_t stage_base, uint64_t n_in, int a_permille, uint8_t* lut_out, uint64_t* part_base_out, uint64_t* counts_out,
+                                       uint32_t* status_out, uint64_t* plan_out) {
+    static_assert(sizeof(DistHalfPlan) == (4 + 3 * (XP_MAX_PARTS / 2)) * sizeof(uint64_t), "plan_out layout documented in include/b200rs.h");
+    if (!dev || !hist_all || !peer_base || !lut_out || !part_base_out || !counts_out || !status_out || !plan_out || world < 1 || world > XP_MAX_PARTS / 2 || rank < 0 ||
+        rank >= world || a_permille < 0 || a_permille > 1000)
+        return B200RS_ERR_INVALID_ARGUMENT;
+    b200rs_device_guard guard(dev);
+    {
+        b200rs_launch_scope scope(dev, "dist_plan_halves", (uint64_t)world * RADIX, (uint64_t)world * RADIX * 8);
+        dist_plan_halves_kernel<<<1, RADIX, 0, dev->stream>>>(reinterpret_cast<const unsigned long long*>(hist_all), world, rank, reinterpret_cast<const unsigned long long*>(peer_base),
+                                                              capacity, stage_base, lut_out, reinterpret_cast<unsigned long long*>(part_base_out),
+                                                              reinterpret_cast<unsigned long long*>(counts_out), status_out, n_in, reinterpret_cast<DistHalfPlan*>(plan_out),
+                                                              (uint32_t)a_permille);
+    }
+    B200RS_CUDA(cudaGetLastError());
+    return B200RS_OK;
+}
+
 extern "C" int b200rs_sort_pairs_u32_devn(b200rs_device* dev, b200rs_pair* inout, uint64_t n_max, const uint64_t* n_dev, int sort_bits,
                                           void* temp, size_t* temp_bytes) {
     return sort_impl<uint2>(dev, reinterpret_cast<uint2*>(inout), n_max, sort_bits, temp, temp_bytes, "pairs",
@@ -2216,14 +2235,9 @@ int dist_sort_pipelined(b200rs_device* dev, const b200rs_dist_comm* comm, const 
         const int rc = comm->allgather(comm->user, hist, gathered, RADIX * 8);
         if (rc != 0) return rc;
     }
-    {
-        b200rs_launch_scope scope(dev, "dist_plan_halves", (uint64_t)world * RADIX, (uint64_t)world * RADIX * 8);
-        dist_plan_halves_kernel<<<1, RADIX, 0, dev->stream>>>(reinterpret_cast<const unsigned long long*>(gathered), world, rank, reinterpret_cast<const unsigned long long*>(peers),
-                                                              recv_capacity_pairs, (unsigned long long)(uintptr_t)stage, lut, reinterpret_cast<unsigned long long*>(part_base),
-                                                              reinterpret_cast<unsigned long long*>(counts_dev), status_dev, n, plan_dev,
-                                                              (uint32_t)b200rs_exp_env("B200RS_DIST_A_PERMILLE", DIST_PIPELINE_A_PERMILLE));
-    }
-    B200RS_CUDA(cudaGetLastError());
+    B200RS_TRY(b200rs_dist_plan_halves(dev, gathered, world, rank, peers, recv_capacity_pairs, (uint64_t)(uintptr_t)stage, n,
+                                       b200rs_exp_env("B200RS_DIST_A_PERMILLE", DIST_PIPELINE_A_PERMILLE), lut, part_base, counts_dev, status_dev,
+                                       reinterpret_cast<uint64_t*>(plan_dev)));
     B200RS_CUDA(cudaMemcpyAsync(dev->pinned_plan, plan_dev, sizeof(DistHalfPlan), cudaMemcpyDeviceToHost, dev->stream));
     B200RS_CUDA(cudaStreamSynchronize(dev->stream));
     const DistHalfPlan plan = *static_cast<const DistHalfPlan*>(dev->pinned_plan);

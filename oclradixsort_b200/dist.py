@@ -82,6 +82,46 @@ def plan_exchange(hist: np.ndarray) -> dict:
             "recv_offset": recv_offset, "bin_offset": bin_offset}
 
 
+def plan_exchange_halves(hist: np.ndarray, a_permille: int = 500) -> dict:
+    """The plan of the PIPELINED partitioned sort (dist_plan_halves_kernel in csrc/b200rs_sort.cu; this is its host mirror
+    and the CPU tests' reference): the digit ranges of plan_exchange(), each cut once more at the digit boundary where half A
+    holds closest to a_permille / 1000 of the destination's pairs (ties to the lower digit).
+
+      bin_to_part[256]      2 * destination + half (0 = A: the lower digits of the destination's range)
+      mids[d]               first digit of destination d's half B
+      part_counts[s, v]     pairs source s sends to part v
+      recv_a[d], recv_b[d]  pairs destination d receives per half
+      part_offset[s, v]     where source s writes inside destination v // 2's receive buffer (pairs): the buffer reads
+                            [A: source 0, source 1, ... | B: source 0, source 1, ...]
+    """
+    base = plan_exchange(hist)
+    hist = np.asarray(hist, dtype=np.int64)
+    P = hist.shape[0]
+    edges = base["edges"]
+    totals = hist.sum(axis=0)
+    cum = np.concatenate([[0], np.cumsum(totals)])
+    mids = []
+    for d in range(P):
+        lo, hi = edges[d], edges[d + 1]
+        tot = int(cum[hi] - cum[lo])
+        ks = np.arange(lo, hi + 1)
+        dist_k = np.abs(1000 * (cum[ks] - cum[lo]) - a_permille * tot)
+        mids.append(int(ks[int(np.argmin(dist_k))]))  # argmin returns the first (lowest digit) of equal distances
+    bin_to_part = np.zeros(NUM_BINS, dtype=np.uint8)
+    part_counts = np.zeros((P, 2 * P), dtype=np.int64)
+    for d in range(P):
+        bin_to_part[edges[d]:mids[d]] = 2 * d
+        bin_to_part[mids[d]:edges[d + 1]] = 2 * d + 1
+        part_counts[:, 2 * d] = hist[:, edges[d]:mids[d]].sum(axis=1)
+        part_counts[:, 2 * d + 1] = hist[:, mids[d]:edges[d + 1]].sum(axis=1)
+    recv_a, recv_b = part_counts[:, 0::2].sum(axis=0), part_counts[:, 1::2].sum(axis=0)
+    before = np.cumsum(part_counts, axis=0) - part_counts  # pairs of lower ranks in the same part
+    part_offset = before.copy()
+    part_offset[:, 1::2] += recv_a[None, :]
+    return {"bin_to_part": bin_to_part, "edges": edges, "mids": mids, "part_counts": part_counts, "recv_a": recv_a, "recv_b": recv_b,
+            "recv_total": recv_a + recv_b, "part_offset": part_offset, "total": base["total"]}
+
+
 class SplitterPlan:
     """Exact quantile splitters from per-source digit histograms, refined one digit per round (pure numpy; every rank
     computes the same plan from the same all-gathered histograms).

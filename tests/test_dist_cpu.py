@@ -195,3 +195,50 @@ def test_splitter_plan_is_exact_stable_and_balanced(P, kind):
     # equal shards: balanced to within ONE source's count of the key a boundary falls on (exact when no key is hot)
     spread = int(res["recv_total"].max() - res["recv_total"].min())
     assert spread <= (2000 if kind in ("two", "hotkey") else 1), (spread, res["recv_total"])
+
+
+def test_halves_plan_two_stable_sorts_equal_one_stable_sort():
+    """The pipelined partitioned sort on the CPU, P simulated ranks: every source partitions its slice by plan_exchange_halves()
+    into the receive buffers' [A: source 0, 1, ... | B: source 0, 1, ...] layout at the plan's offsets, every destination sorts
+    its two halves separately (stable); the concatenation must be the oracle's stable sort of the whole input."""
+    from oclradixsort_b200.dist import plan_exchange_halves
+    rng = np.random.default_rng(21)
+    for P, n, kind, a in ((2, 5000, "uniform", 500), (3, 4001, "skewtop", 500), (8, 3000, "uniform", 350), (5, 2000, "onedigit", 500), (4, 1, "uniform", 500),
+                          (16, 700, "lowentropy", 650)):
+        slices = []
+        for r in range(P):
+            m = n + 3 * r
+            keys = rng.integers(0, 2**32, size=m, dtype=np.uint64).astype(np.uint32)
+            if kind == "skewtop":
+                keys >>= np.uint32(2 * r)
+            elif kind == "onedigit":
+                keys = (keys & np.uint32(0x00FFFFFF)) | np.uint32(0x33000000)
+            elif kind == "lowentropy":
+                keys = (keys & np.uint32(0x0F00000F)) * np.uint32(0x11)
+            kv = np.empty((m, 2), dtype=np.uint32)
+            kv[:, 0], kv[:, 1] = keys, np.arange(m, dtype=np.uint32) + np.uint32(r << 20)
+            slices.append(kv)
+        hist = np.stack([np.bincount(kv[:, 0] >> 24, minlength=256) for kv in slices])
+        plan = plan_exchange_halves(hist, a)
+        # plan invariants
+        assert np.all(np.diff(plan["bin_to_part"].astype(int)) >= 0) and plan["part_counts"].sum() == sum(len(kv) for kv in slices)
+        assert np.array_equal(plan["recv_a"] + plan["recv_b"], plan["recv_total"])
+        recv = [np.full((int(plan["recv_total"][d]), 2), 0xFFFFFFFF, dtype=np.uint32) for d in range(P)]
+        filled = [np.zeros(int(plan["recv_total"][d]), dtype=bool) for d in range(P)]
+        for s_rank, kv in enumerate(slices):
+            part = plan["bin_to_part"][kv[:, 0] >> 24]
+            for v in range(2 * P):
+                run = kv[part == v]  # boolean indexing keeps input order: the stable partition
+                assert len(run) == plan["part_counts"][s_rank, v]
+                off = int(plan["part_offset"][s_rank, v])
+                assert not filled[v // 2][off:off + len(run)].any()
+                recv[v // 2][off:off + len(run)] = run
+                filled[v // 2][off:off + len(run)] = True
+        assert all(f.all() for f in filled)
+        outs = []
+        for d in range(P):
+            ra = int(plan["recv_a"][d])
+            outs.append(po.sort_pairs(recv[d][:ra].copy()))
+            outs.append(po.sort_pairs(recv[d][ra:].copy()))
+        whole = np.concatenate(slices)
+        assert np.array_equal(np.concatenate(outs), po.sort_pairs(whole.copy())), (P, n, kind, a)

@@ -87,6 +87,69 @@ def test_device_plan_matches_host_plan():
     ob.DeviceUtils.deallocate(d)
 
 
+def test_device_halves_plan_matches_host_plan():
+    """dist_plan_halves_kernel (the plan of the pipelined partitioned sort) against plan_exchange_halves() for every rank of
+    P = 1 .. 16, balanced / skewed / one-digit / empty histograms and three shares of half A."""
+    import torch
+
+    import oclradixsort_b200 as ob
+    from oclradixsort_b200._lib import check, lib
+    from oclradixsort_b200.dist import plan_exchange_halves
+    d = ob.DeviceUtils.allocate(ob.TYPE_CL, 0, cuda_stream=torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(12)
+    stage_base = 1 << 45
+    for P in (1, 2, 3, 8, 16):
+        for kind in ("uniform", "skew", "onebin", "empty"):
+            hist = rng.integers(0, 5000, size=(P, 256)).astype(np.int64)
+            if kind == "skew":
+                hist[:, 10:20] *= 300
+            elif kind == "onebin":
+                hist[:] = 0
+                hist[:, 77] = 1234
+            elif kind == "empty":
+                hist[:] = 0
+            for a in (500, 300, 1000):
+                plan = plan_exchange_halves(hist, a)
+                peers = np.arange(P, dtype=np.int64) * (1 << 40) + (1 << 30)
+                cap = int(plan["recv_total"].max())
+                for me in range(P):
+                    g = torch.from_numpy(hist.reshape(-1).copy()).cuda()
+                    pd = torch.from_numpy(peers).cuda()
+                    lut = torch.zeros(256, dtype=torch.uint8, device="cuda")
+                    base = torch.zeros(64, dtype=torch.int64, device="cuda")
+                    cnts = torch.zeros(2, dtype=torch.int64, device="cuda")
+                    st = torch.ones(1, dtype=torch.int32, device="cuda")
+                    out = torch.zeros(52, dtype=torch.int64, device="cuda")
+                    check(lib().b200rs_dist_plan_halves(d.handle, ctypes.c_void_p(g.data_ptr()), P, me, ctypes.c_void_p(pd.data_ptr()), cap, stage_base, 4242, a,
+                                                        ctypes.c_void_p(lut.data_ptr()), ctypes.c_void_p(base.data_ptr()), ctypes.c_void_p(cnts.data_ptr()),
+                                                        ctypes.c_void_p(st.data_ptr()), ctypes.c_void_p(out.data_ptr())), "b200rs_dist_plan_halves")
+                    torch.cuda.synchronize()
+                    o = out.cpu().numpy()
+                    assert np.array_equal(lut.cpu().numpy(), plan["bin_to_part"]), (P, kind, a)
+                    assert int(st.item()) == 0 and o[0] == 0
+                    assert cnts.cpu().tolist() == [4242, int(plan["recv_total"][me])]
+                    assert (o[1], o[2], o[3]) == (plan["recv_total"][me], plan["recv_a"][me], plan["recv_b"][me]), (P, kind, a, me)
+                    got_base = base.cpu().numpy()[:2 * P]
+                    running = 0
+                    for dest in range(P):
+                        final_b = peers[dest] + 8 * plan["part_offset"][me, 2 * dest + 1]
+                        assert got_base[2 * dest] == peers[dest] + 8 * plan["part_offset"][me, 2 * dest]
+                        assert o[36 + dest] == final_b
+                        if dest == me:
+                            assert got_base[2 * dest + 1] == final_b and o[20 + dest] == 0
+                        else:  # staged: runs in destination order, each starting on a 128-byte boundary
+                            assert got_base[2 * dest + 1] == stage_base + 8 * running and o[4 + dest] == running
+                            assert o[20 + dest] == plan["part_counts"][me, 2 * dest + 1]
+                            running += (int(plan["part_counts"][me, 2 * dest + 1]) + 15) // 16 * 16
+                if cap > 0:  # one pair less capacity than needed: aborted
+                    check(lib().b200rs_dist_plan_halves(d.handle, ctypes.c_void_p(g.data_ptr()), P, 0, ctypes.c_void_p(pd.data_ptr()), cap - 1, stage_base, 4242, a,
+                                                        ctypes.c_void_p(lut.data_ptr()), ctypes.c_void_p(base.data_ptr()), ctypes.c_void_p(cnts.data_ptr()),
+                                                        ctypes.c_void_p(st.data_ptr()), ctypes.c_void_p(out.data_ptr())), "b200rs_dist_plan_halves")
+                    torch.cuda.synchronize()
+                    assert cnts.cpu().tolist() == [0, 0] and int(st.item()) == 1 and int(out[0].item()) == 1
+    ob.DeviceUtils.deallocate(d)
+
+
 def test_partitioned_sort_two_gpus_nccl():
     import torch
     if torch.cuda.device_count() < 2:
