@@ -175,7 +175,7 @@ int b200rs_exchange_pairs_by_splitters(b200rs_device* dev, const b200rs_pair* in
 int b200rs_filtered_histograms_pairs(b200rs_device* dev, const b200rs_pair* in, uint64_t n, int shift, const uint32_t* prefixes, int count,
                                      uint64_t* hist_out);
 /*
- * Exchange plan computed on the device, so the multi-GPU sort needs no host round trip: from the all-gathered
+ * Exchange plan computed on the device (the unpipelined multi-GPU sort needs no host round trip): from the all-gathered
  * top-digit histograms hist_all[world][256] it derives contiguous digit ranges per rank (about N/world pairs each),
  * lut_out[256] (digit -> destination rank), part_base_out[256] (where THIS rank's pairs for destination d start:
  * peer_base[d] + 8 * pairs sent to d by lower ranks), counts_out[0] = n_in (or 0 if aborted), counts_out[1] = pairs this

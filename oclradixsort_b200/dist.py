@@ -15,6 +15,12 @@ Steps 1-5 are ONE C call, b200rs_dist_sort_pairs_u32, which takes the two collec
 communication library); this module supplies torch.distributed for them.  exchange="nccl" keeps the baseline: partition
 into a local send buffer + dist.all_to_all_single.
 
+From 2^22 pairs of receive capacity the C call runs steps 2-5 PIPELINED (plan_exchange_halves() below is the host mirror
+of its plan): every destination's digit range is cut into halves A | B; the kernel of step 3 stores half A over NVLink
+and stages half B locally; copy engines move half B to the peers while half A is already being sorted on a second
+stream; half B is sorted when it has landed (two barriers instead of one; the call reads the plan back once, so it
+returns after the plan kernel has run -- everything after that is stream-ordered).
+
 Skew.  Digit ranges cannot split a hot top digit; when the plan of step 2 would overflow a receive buffer the sort is
 re-planned with EXACT QUANTILE SPLITTERS (SplitterPlan): three more rounds of 256-bin histograms restricted to the bins
 the boundaries fall in narrow every boundary down to one 32-bit key, and a key that is itself too frequent is split by
@@ -440,10 +446,11 @@ class DistributedPairSorter:
         return pairs
 
     def sort_async(self, pairs, n: int):
-        """p2p/dest only: enqueue the whole partitioned sort without any host round trip -- one call of
-        b200rs_dist_sort_pairs_u32 (histogram -> all-gather -> on-device plan -> fused partition + peer stores -> barrier ->
-        local sort with a device-side count).  Returns the receive buffer; call finish() for the element count (it
-        synchronises; a plan that overflowed a receive buffer exchanged nothing and reports status 1)."""
+        """p2p/dest only: enqueue the whole partitioned sort -- one call of b200rs_dist_sort_pairs_u32 (histogram ->
+        all-gather -> on-device plan -> fused partition + peer stores -> barrier -> local sort; pipelined in two halves from
+        2^22 pairs of capacity, see the module docstring; below that no host round trip at all).  Returns the receive buffer;
+        call finish() for the element count (it synchronises; a plan that overflowed a receive buffer exchanged nothing and
+        reports status 1)."""
         assert self.exchange == "p2p" and self.layout == "dest"
         src = self._as_tensor(pairs, n)
         self.ops.dist_sort_async(src, n, self.dist, self.world, self.rank, self.peers, self.capacity, self._flag)
