@@ -221,8 +221,11 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
+    numa = None
     if world > 1:
         import torch.distributed as dist
+        from oclradixsort_b200.dist import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: every rank's host buffers next to its GPU
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = 1 << args.log2_pairs_per_gpu
@@ -602,7 +605,7 @@ def main() -> None:
             "config": {"workload": f"kv_sort_u32u32_uniform_2^{args.log2_pairs_per_gpu}_pairs_per_gpu", "sort_bits": 32,
                        "pairs_per_gpu": n, "l2": "every step sorts a different 2 GiB buffer (inputs larger than L2, no flush needed)",
                        "parallelism": "single GPU" if world == 1 else f"msd-partitioned over {world} GPUs (top-digit histogram, all-gather of the histograms, on-device plan with two halves per destination; one exchange kernel: half A by peer stores over NVLink, half B staged and moved by copy engines while half A is sorted on a second stream; local LSD sorts)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "numa_rank0": numa,
             "step_ms_rank0": [round(x, 3) for x in step_ms],
         }
         if keys_line:

@@ -581,6 +581,34 @@ class DistributedPairSorter:
         self.ops.release()
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates pinned host buffers: with one
+    process per GPU the staging memory of every rank then sits on the socket next to its GPU (first touch) instead of wherever
+    the launcher started the process, and host <-> device copies do not cross the socket interconnect.  Best effort: returns
+    {"node": N, "cpus": count} or None when the topology cannot be read (no sysfs entry, single node, no permission)."""
+    import os
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except Exception:  # noqa: BLE001 -- an optimisation, never a requirement
+        return None
+
+
 def _tensor_from_ptr(torch, ptr: int, n: int, device):
     """Zero-copy int64 view of `n` pairs at device address `ptr` (CUDA array interface)."""
 
