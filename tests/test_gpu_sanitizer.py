@@ -1,5 +1,5 @@
 """compute-sanitizer memcheck over small instances of every entry point (tools/sanitize_small.py, which also checks every
-result against numpy).  racecheck and synccheck of the same program are recorded in profiles/r1c_compute_sanitizer.txt."""
+result against numpy).  racecheck and synccheck of the same program are recorded in profiles/r2_final_compute_sanitizer.txt."""
 import os
 import shutil
 import subprocess
