@@ -94,6 +94,10 @@ int b200rs_memset(b200rs_device* dev, void* ptr, int byte_value, size_t bytes); 
  * `inout`.  sort_bits in [0,32]; the reference's GPU path accepts multiples of 4 (Pprims.cpp:330),
  * every width is accepted here.  Any n >= 0 (the reference's key-only kernels need n % 256 == 0,
  * Pprims.cpp:327).  Replaces Pprims::radixSort(device, Buffer<u32>&, n, sortBits), Pprims.cpp:304-406.
+ * Asynchronous like every entry point, with one exception: a 32-bit sort of 201 326 592 to 2^30 - 1 keys first takes a joint
+ * histogram of the top 16 bits to choose between the key-only MSD pipeline and the LSD passes (the results are the same bits
+ * either way: without a payload nothing distinguishes equal keys); the call returns once that histogram has run on the
+ * device (a tenth of the sort) and the remaining kernels are queued -- it waits for work queued earlier on the stream too.
  */
 int b200rs_sort_keys_u32(b200rs_device* dev, uint32_t* inout, uint64_t n, int sort_bits, void* temp, size_t* temp_bytes);
 /*
