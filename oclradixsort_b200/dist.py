@@ -502,6 +502,7 @@ class DistributedPairSorter:
         if self.exchange == "p2p" and self.layout == "dest" and hasattr(self.ops, "dist_sort_async"):
             out = self.sort_async(pairs, n)
             m, status = self.ops.read_counts()
+            self.last_path = "digit ranges" if status == 0 else "quantile splitters"
             if status == 0:
                 return out[:m], m
             return self.sort_with_splitters(pairs, n)  # the digit-range plan overflowed (skew): nothing was exchanged
