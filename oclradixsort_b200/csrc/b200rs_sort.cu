@@ -2226,7 +2226,8 @@ int dist_sort_pipelined(b200rs_device* dev, const b200rs_dist_comm* comm, const 
         B200RS_CUDA(cudaHostAlloc(&dev->pinned_plan, sizeof(DistHalfPlan), cudaHostAllocDefault));
     }
     cudaEvent_t ev_exchanged = dev->ev_pipe[0], ev_a_landed = dev->ev_pipe[3], ev_a_sorted = dev->ev_pipe[4];
-    const int copy_streams = b200rs_exp_env("B200RS_DIST_COPY_STREAMS", COPY_STREAMS) < COPY_STREAMS ? (b200rs_exp_env("B200RS_DIST_COPY_STREAMS", COPY_STREAMS) < 1 ? 1 : b200rs_exp_env("B200RS_DIST_COPY_STREAMS", COPY_STREAMS)) : COPY_STREAMS;
+    int copy_streams = b200rs_exp_env("B200RS_DIST_COPY_STREAMS", COPY_STREAMS);
+    copy_streams = copy_streams < 1 ? 1 : (copy_streams > COPY_STREAMS ? COPY_STREAMS : copy_streams);
 
     B200RS_CUDA(cudaMemcpyAsync(peers, recv_base, (size_t)world * 8, cudaMemcpyHostToDevice, dev->stream));  // (pageable source: staged by the runtime before the call returns)
     B200RS_TRY(b200rs_digit_histogram_pairs(dev, in, n, 24, 8, hist));

@@ -242,3 +242,14 @@ def test_halves_plan_two_stable_sorts_equal_one_stable_sort():
             outs.append(po.sort_pairs(recv[d][ra:].copy()))
         whole = np.concatenate(slices)
         assert np.array_equal(np.concatenate(outs), po.sort_pairs(whole.copy())), (P, n, kind, a)
+
+
+def test_numa_binding_is_best_effort_without_a_gpu():
+    """bind_to_gpu_numa_node never raises: without a CUDA device (this container) or without a NUMA entry it returns None and
+    leaves the process affinity alone."""
+    from oclradixsort_b200.dist import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    res = bind_to_gpu_numa_node(0)
+    assert res is None or (isinstance(res, dict) and res["cpus"] >= 1)
+    if res is None:
+        assert os.sched_getaffinity(0) == before
