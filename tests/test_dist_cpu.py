@@ -253,3 +253,39 @@ def test_numa_binding_is_best_effort_without_a_gpu():
     assert res is None or (isinstance(res, dict) and res["cpus"] >= 1)
     if res is None:
         assert os.sched_getaffinity(0) == before
+
+
+def test_exchange_plans_hold_their_invariants_on_random_histograms():
+    """Property check (seeded random histograms incl. sparse, constant and single-source ones) of the two host plans every rank
+    derives: digit ranges are contiguous and cover all 256 digits, halves cut each range once, send / receive counts add up,
+    offsets tile every receive buffer exactly once in [A: source 0.. | B: source 0..] order."""
+    from oclradixsort_b200.dist import plan_exchange_halves
+    rng = np.random.default_rng(99)
+    for trial in range(120):
+        P = int(rng.integers(1, 17))
+        mode = trial % 4
+        hist = rng.integers(0, 1000, size=(P, 256)).astype(np.int64)
+        if mode == 1:
+            hist *= (rng.random((P, 256)) < 0.03)          # sparse: most digits empty
+        elif mode == 2:
+            hist[:] = 7                                     # every digit equally full
+        elif mode == 3:
+            hist[1:] = 0                                    # one source holds everything
+        a = int(rng.choice([0, 250, 500, 900, 1000]))
+        base, plan = plan_exchange(hist), plan_exchange_halves(hist, a)
+        edges, mids = plan["edges"], plan["mids"]
+        assert edges == base["edges"] and edges[0] == 0 and edges[-1] == 256 and all(x <= y for x, y in zip(edges, edges[1:]))
+        assert all(edges[d] <= mids[d] <= edges[d + 1] for d in range(P))
+        assert np.array_equal(plan["bin_to_part"] // 2, base["bin_to_rank"])
+        assert np.array_equal(plan["part_counts"][:, 0::2] + plan["part_counts"][:, 1::2], base["send_counts"])
+        assert np.array_equal(plan["recv_total"], base["recv_total"]) and int(plan["recv_total"].sum()) == int(hist.sum())
+        for d in range(P):  # the (source, half) runs tile destination d's buffer without gaps or overlap, A before B, sources in order
+            runs = sorted((int(plan["part_offset"][s_, 2 * d + h]), int(plan["part_counts"][s_, 2 * d + h]), h, s_) for h in (0, 1) for s_ in range(P))
+            at = 0
+            for off, cnt, h, s_ in runs:
+                if cnt:
+                    assert off == at, (trial, d, h, s_)
+                    at += cnt
+            assert at == int(plan["recv_total"][d])
+            order = [(h, s_) for off, cnt, h, s_ in runs if cnt]
+            assert order == sorted(order)
