@@ -188,7 +188,8 @@ def _device_ops():
 
 def test_exchange_kernel_matches_numpy_stable_partition():
     """b200rs_exchange_pairs (the few-parts kernel with bulk copies) on one GPU: the parts' base addresses point into one
-    local buffer, so the result must equal numpy's stable partition; sizes around the 2048-pair tile, 1..32 parts (4 and 5 part bits), runs
+    local buffer, so the result must equal numpy's stable partition; sizes around the tile shapes tried (2048 / 4096 pairs; the 3584-pair tile's edges are in
+    tools/sanitize_small.py), 1..32 parts (4 and 5 part bits), runs
     that start on odd element boundaries (ragged 16-byte ends), empty parts."""
     import torch
 
